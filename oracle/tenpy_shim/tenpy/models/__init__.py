@@ -1,0 +1,1 @@
+"""tenpy shim subpackage (see tenpy/__init__.py)."""
