@@ -1,0 +1,27 @@
+import json
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box with -m gpu)')
+
+
+@pytest.fixture(scope='session')
+def golden():
+    with open(os.path.join(ROOT, 'tests', 'golden', 'reference_golden.json')) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope='session')
+def engine():
+    """The product package; fails loudly if the CUDA library is missing."""
+    import time_crystal_tensor_network_b200 as pkg
+    pkg._lib.load()
+    return pkg

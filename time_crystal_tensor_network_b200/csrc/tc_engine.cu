@@ -1,0 +1,878 @@
+// tc_engine.cu -- C ABI (include/tc_b200.h) of the B200-native kicked-Ising Floquet/TEBD engine.
+//
+// One context = an ensemble of R independent chains on one GPU.  Per two-site update (the unit the
+// reference executes through MPS.apply_local_op, src/models/kicked_ising.py:162-188) the device runs
+//   K1  C = gate . (kick? B_i)(kick? B_{i+1})          DMMA GEMM, kick fused into the operand loads,
+//       theta = S_i C                                  diagonal Ising phase fused into the epilogue
+//   K2  J^H theta = Sigma V^H                          one-sided Jacobi on rows (tc_jacobi.cuh)
+//       sort, truncate, renormalise, B_{i+1} = V_k^H   in-kernel
+//   K3  B_i = C V_k / |Sigma_k|                        DMMA GEMM (inverse-free update)
+// for every bond of a parity class and every chain in one launch each.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/tc_b200.h"
+#include "tc_common.cuh"
+#include "tc_gemm.cuh"
+#include "tc_jacobi.cuh"
+#include "tc_observe.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// errors / bookkeeping
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(const char *fmt, const char *a = "", const char *b = "") {
+  char buf[512];
+  snprintf(buf, sizeof(buf), fmt, a, b);
+  g_err = buf;
+  return 1;
+}
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) return fail("CUDA error: %s at %s", cudaGetErrorString(e_), #call); \
+  } while (0)
+#define LAUNCHED()                                                                   \
+  do {                                                                               \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                              \
+    cudaError_t e_ = cudaGetLastError();                                             \
+    if (e_ != cudaSuccess) return fail("kernel launch failed: %s", cudaGetErrorString(e_)); \
+  } while (0)
+
+struct tc_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false, own_arena = false;
+  void *arena = nullptr;
+  size_t arena_bytes = 0;
+  TcDev d{};
+  cplx *gates_dev = nullptr, *kick_dev = nullptr;  // non-const aliases of d.gates / d.kick
+  cplx *op_scratch = nullptr;                      // 32 cplx: caller-supplied operators
+  cplx *E0 = nullptr, *E1 = nullptr, *Tt = nullptr;  // transfer contraction scratch
+  double *small_out = nullptr;                       // 8 doubles
+  bool have_model = false;
+  // record buffers for tc_floquet_run_host
+  void *rec = nullptr;
+  size_t rec_bytes = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// arena layout
+// ------------------------------------------------------------------------------------------------
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct Layout {
+  size_t B, S, chi, init_idx, gates, kick, trunc_err, flags, Cw, Xw, ww, perm, knew, renorm, op, E0, E1, Tt,
+      small_out, total;
+  int ws_chains, nbmax, n2;
+};
+
+static Layout make_layout(int L, int chi_cap, int R) {
+  Layout o{};
+  const size_t cs = sizeof(cplx);
+  o.n2 = 2 * chi_cap;
+  o.nbmax = L / 2 > 0 ? L / 2 : 1;
+  const size_t site = (size_t)chi_cap * 2 * chi_cap, slot = (size_t)o.n2 * o.n2;
+  size_t budget = (size_t)64 << 30;
+  if (const char *e = getenv("TC_WS_BYTES")) budget = strtoull(e, nullptr, 10);
+  const size_t per_chain = (size_t)o.nbmax * (2 * slot * cs + o.n2 * (sizeof(double) + sizeof(int)) + 16);
+  long long wc = (long long)(budget / per_chain);
+  if (wc < 1) wc = 1;
+  if (wc > R) wc = R;
+  o.ws_chains = (int)wc;
+  const size_t slots = (size_t)o.ws_chains * o.nbmax;
+  size_t p = 0;
+  auto take = [&](size_t bytes) {
+    size_t at = p;
+    p = align_up(p + bytes);
+    return at;
+  };
+  o.B = take((size_t)R * L * site * cs);
+  o.S = take((size_t)R * (L + 1) * chi_cap * sizeof(double));
+  o.chi = take((size_t)R * (L + 1) * sizeof(int));
+  o.init_idx = take((size_t)R * L);
+  o.gates = take((size_t)R * (L > 1 ? L - 1 : 1) * 16 * cs);
+  o.kick = take((size_t)R * 4 * cs);
+  o.trunc_err = take((size_t)R * (L + 1) * sizeof(double));
+  o.flags = take(8 * sizeof(int));
+  o.Cw = take(slots * slot * cs);
+  o.Xw = take(slots * slot * cs);
+  o.ww = take(slots * o.n2 * sizeof(double));
+  o.perm = take(slots * o.n2 * sizeof(int));
+  o.knew = take(slots * sizeof(int));
+  o.renorm = take(slots * sizeof(double));
+  o.op = take(32 * cs);
+  o.E0 = take((size_t)chi_cap * chi_cap * cs);
+  o.E1 = take((size_t)chi_cap * chi_cap * cs);
+  o.Tt = take((size_t)chi_cap * 2 * chi_cap * cs);
+  o.small_out = take(8 * sizeof(double));
+  o.total = p;
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM policies
+// ------------------------------------------------------------------------------------------------
+// K1: T[(a,p0),(p1,b)] = sum_m (kick B_i)[a,p0,m] (kick B_{i+1})[m,p1,b]; diagonal gate: C = phase T,
+// theta = S_i C written in the epilogue; general gate: raw T is stored and gate_mix_kernel follows.
+struct ThetaPolicy {
+  int M, N, K, chiM, chiR;
+  const cplx *Bi, *Bn;
+  cplx *C, *X;
+  const double *S;
+  cplx k00, k01, k10, k11, g0, g1, g2, g3;
+  bool kickL, kickR, diag;
+  static constexpr bool A_KCONTIG = true, B_KCONTIG = false;
+  __device__ bool init(const TcDev &d, const LayerArgs &a, int jb, int ry) {
+    Bond b;
+    if (!get_bond(d, a, jb, ry, b)) return false;
+    M = b.M;
+    N = b.N;
+    K = b.chiM;
+    chiM = b.chiM;
+    chiR = b.chiR;
+    Bi = site_ptr(d, b.r, b.i);
+    Bn = site_ptr(d, b.r, b.i + 1);
+    C = d.Cw + b.slot * d.slot_stride;
+    X = d.Xw + b.slot * d.slot_stride;
+    S = S_ptr(d, b.r, b.i);
+    kickL = (a.kick_mode & 1) != 0;
+    kickR = kickL || ((a.kick_mode & 2) && b.i == d.L - 2);
+    const cplx *kk = d.kick + (size_t)b.r * 4;
+    k00 = kk[0];
+    k01 = kk[1];
+    k10 = kk[2];
+    k11 = kk[3];
+    diag = a.diag != 0;
+    const cplx *g = a.gate_override ? a.gate_override : d.gates + ((size_t)b.r * (d.L - 1) + b.i) * 16;
+    g0 = g[0];
+    g1 = g[5];
+    g2 = g[10];
+    g3 = g[15];
+    return true;
+  }
+  __device__ __forceinline__ cplx A(int row, int k) const {
+    if (row >= M || k >= K) return cmake(0.0, 0.0);
+    if (!kickL) return Bi[(size_t)row * chiM + k];
+    const size_t base = (size_t)(row & ~1) * chiM + k;
+    const cplx x0 = Bi[base], x1 = Bi[base + chiM];
+    cplx y = cmul((row & 1) ? k10 : k00, x0);
+    cfma(y, (row & 1) ? k11 : k01, x1);
+    return y;
+  }
+  __device__ __forceinline__ cplx B(int col, int k) const {
+    if (col >= N || k >= K) return cmake(0.0, 0.0);
+    const int p = col >= chiR, bb = col - p * chiR;
+    if (!kickR) return Bn[(size_t)(2 * k + p) * chiR + bb];
+    const size_t base = (size_t)(2 * k) * chiR + bb;
+    const cplx x0 = Bn[base], x1 = Bn[base + chiR];
+    cplx y = cmul(p ? k10 : k00, x0);
+    cfma(y, p ? k11 : k01, x1);
+    return y;
+  }
+  __device__ __forceinline__ void store(int row, int col, cplx v) const {
+    const size_t o = (size_t)row * N + col;
+    if (diag) {
+      const int p0 = row & 1, p1 = col >= chiR;
+      const cplx ph = p0 ? (p1 ? g3 : g2) : (p1 ? g1 : g0);
+      const cplx c = cmul(ph, v);
+      C[o] = c;
+      X[o] = cscale(c, S[row >> 1]);
+    } else {
+      C[o] = v;
+    }
+  }
+};
+
+// general 4x4 gate on the raw two-site tensor, then theta = S_i C.  grid (ceil(chiL*chiR/256), nb, nr)
+__global__ void __launch_bounds__(256) gate_mix_kernel(TcDev d, LayerArgs a) {
+  Bond b;
+  if (!get_bond(d, a, blockIdx.y, blockIdx.z, b)) return;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= b.chiL * b.chiR) return;
+  const int al = e / b.chiR, be = e - al * b.chiR;
+  const cplx *g = a.gate_override ? a.gate_override : d.gates + ((size_t)b.r * (d.L - 1) + b.i) * 16;
+  cplx *C = d.Cw + b.slot * d.slot_stride, *X = d.Xw + b.slot * d.slot_stride;
+  const double s = S_ptr(d, b.r, b.i)[al];
+  size_t o[4];
+  cplx t[4];
+  for (int q = 0; q < 4; ++q) {
+    o[q] = (size_t)(2 * al + (q >> 1)) * b.N + (q & 1) * b.chiR + be;
+    t[q] = C[o[q]];
+  }
+  for (int p = 0; p < 4; ++p) {
+    cplx acc = cmake(0.0, 0.0);
+    for (int q = 0; q < 4; ++q) cfma(acc, g[p * 4 + q], t[q]);
+    C[o[p]] = acc;
+    X[o[p]] = cscale(acc, s);
+  }
+}
+
+// K3: B_i[(a,p0),k] = sum_col C[(a,p0),col] conj(B_{i+1}[k,col]) / renorm
+struct BLPolicy {
+  int M, N, K;
+  const cplx *C, *Bn;
+  cplx *Bi;
+  double inv;
+  static constexpr bool A_KCONTIG = true, B_KCONTIG = true;
+  __device__ bool init(const TcDev &d, const LayerArgs &a, int jb, int ry) {
+    Bond b;
+    if (!get_bond(d, a, jb, ry, b)) return false;
+    M = b.M;
+    N = b.chiM;  // already the truncated bond dimension
+    K = b.N;
+    C = d.Cw + b.slot * d.slot_stride;
+    Bn = site_ptr(d, b.r, b.i + 1);
+    Bi = site_ptr(d, b.r, b.i);
+    inv = 1.0 / d.renorm[b.slot];
+    return true;
+  }
+  __device__ __forceinline__ cplx A(int row, int k) const {
+    return (row < M && k < K) ? C[(size_t)row * K + k] : cmake(0.0, 0.0);
+  }
+  __device__ __forceinline__ cplx B(int col, int k) const {
+    return (col < N && k < K) ? cconj(Bn[(size_t)col * K + k]) : cmake(0.0, 0.0);
+  }
+  __device__ __forceinline__ void store(int row, int col, cplx v) const {
+    Bi[(size_t)row * N + col] = cscale(v, inv);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// FP64 throughput probes (roofline denominator)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) probe_fma_kernel(double *out, int iters) {
+  double a[8];
+  const double x = 1.0000001, y = 1e-9 * threadIdx.x;
+  for (int k = 0; k < 8; ++k) a[k] = k + y;
+  for (int it = 0; it < iters; ++it)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = fma(a[k], x, y);
+  double s = 0.0;
+  for (int k = 0; k < 8; ++k) s += a[k];
+  if (s == 123.456) out[0] = s;
+}
+__global__ void __launch_bounds__(256) probe_dmma_kernel(double *out, int iters) {
+  double c[8][2];
+  const double x = 1.0 + 1e-9 * threadIdx.x, y = 1e-9;
+  for (int k = 0; k < 8; ++k) c[k][0] = c[k][1] = 0.0;
+  for (int it = 0; it < iters; ++it)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tcg::dmma(c[k][0], c[k][1], x, y);
+  double s = 0.0;
+  for (int k = 0; k < 8; ++k) s += c[k][0] + c[k][1];
+  if (s == 123.456) out[0] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+static int check_ctx(tc_ctx *c) {
+  if (!c) return fail("null context");
+  CK(cudaSetDevice(c->device));
+  return 0;
+}
+#define CTX(c)                 \
+  do {                         \
+    if (check_ctx(c)) return 1; \
+  } while (0)
+
+static bool gates_all_diagonal(const double *g, size_t n_gates) {
+  for (size_t k = 0; k < n_gates; ++k)
+    for (int p = 0; p < 4; ++p)
+      for (int q = 0; q < 4; ++q)
+        if (p != q && (g[(k * 16 + p * 4 + q) * 2] != 0.0 || g[(k * 16 + p * 4 + q) * 2 + 1] != 0.0)) return false;
+  return true;
+}
+
+// one group of two-site updates: bonds first_site + 2 jb, jb < nb, on chains [r_lo, r_hi)
+static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int kick_mode, const cplx *gate_override,
+                     int diag) {
+  if (nb <= 0 || r_hi <= r_lo) return 0;
+  const TcDev &d = c->d;
+  const int tiles1 = (d.n2 + tcg::BM - 1) / tcg::BM;
+  const int tiles = tiles1 * tiles1;
+  for (int r0 = r_lo; r0 < r_hi; r0 += d.ws_chains) {
+    const int nr = (r_hi - r0) < d.ws_chains ? (r_hi - r0) : d.ws_chains;
+    LayerArgs a{first_site, 2, nb, r0, nr, kick_mode, gate_override, diag};
+    tcg::gemm_kernel<ThetaPolicy><<<dim3(tiles, nb, nr), tcg::NT, 0, c->stream>>>(d, a);
+    LAUNCHED();
+    if (!diag) {
+      const int gx = (d.chi_cap * d.chi_cap + 255) / 256;
+      gate_mix_kernel<<<dim3(gx, nb, nr), 256, 0, c->stream>>>(d, a);
+      LAUNCHED();
+    }
+    tcj::jacobi_rows_kernel<<<dim3(nb, nr), tcj::NT, d.n2 * sizeof(double), c->stream>>>(d, a);
+    LAUNCHED();
+    tcj::finalize_kernel<<<dim3(nb, nr), tcj::NT, d.n2 * sizeof(double), c->stream>>>(d, a);
+    LAUNCHED();
+    tcg::gemm_kernel<BLPolicy><<<dim3(tiles, nb, nr), tcg::NT, 0, c->stream>>>(d, a);
+    LAUNCHED();
+  }
+  return 0;
+}
+
+static int run_layer(tc_ctx *c, int parity, int kick_mode) {
+  const int L = c->d.L;
+  if (L < 2) return 0;
+  const int nb = (L - 1 - parity + 1) / 2;  // bonds parity, parity+2, ... <= L-2
+  return run_bonds(c, parity, nb, 0, c->d.R, kick_mode, nullptr, c->d.gates_diag);
+}
+
+static int run_kick_all(tc_ctx *c) {
+  tco::one_site_kernel<<<dim3(c->d.L, c->d.R), 256, 0, c->stream>>>(c->d, 0, 0, nullptr);
+  LAUNCHED();
+  return 0;
+}
+
+// even, odd, kick (fused into the loads of the second Ising layer), even, odd
+static int run_period(tc_ctx *c) {
+  const int L = c->d.L;
+  if (L < 2) return run_kick_all(c);
+  if (run_layer(c, 0, 0)) return 1;
+  if (run_layer(c, 1, 0)) return 1;
+  if (run_layer(c, 0, 1)) return 1;  // the even bonds cover sites 0 .. 2*floor(L/2)-1
+  if (L == 2) return 0;
+  return run_layer(c, 1, (L & 1) ? 2 : 0);  // odd L: site L-1 is the right site of the last odd bond
+}
+
+static int measure_into(tc_ctx *c, double *rdm, double *Z, double *ent, double *ov, int32_t *chi) {
+  const TcDev &d = c->d;
+  if (rdm || Z || ent) {
+    tco::measure_kernel<<<dim3(d.L, d.R), tco::NT, 0, c->stream>>>(d, rdm, Z, ent);
+    LAUNCHED();
+  }
+  if (ov) {
+    tco::overlap_product_kernel<<<d.R, tco::NT, 2 * d.chi_cap * sizeof(cplx), c->stream>>>(d, ov);
+    LAUNCHED();
+  }
+  if (chi) {
+    tco::chi_record_kernel<<<64, 256, 0, c->stream>>>(d, chi);
+    LAUNCHED();
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int tc_version(void) { return 100; }
+const char *tc_last_error(void) { return g_err.c_str(); }
+int tc_device_count(int *count) {
+  CK(cudaGetDeviceCount(count));
+  return 0;
+}
+long long tc_launch_count(void) { return g_launches.load(); }
+
+size_t tc_ctx_arena_bytes(int L, int chi_cap, int R) {
+  if (L < 1 || chi_cap < 1 || R < 1) return 0;
+  return make_layout(L, chi_cap, R).total;
+}
+
+int tc_ctx_create(int device, int L, int chi_cap, int R, void *arena, size_t arena_bytes, void *stream, tc_ctx **out) {
+  if (!out) return fail("tc_ctx_create: out is null");
+  if (L < 1 || chi_cap < 1 || R < 1) return fail("tc_ctx_create: L, chi_cap, R must be >= 1");
+  if (R > 65535) return fail("tc_ctx_create: R > 65535 chains per context");
+  CK(cudaSetDevice(device));
+  Layout lo = make_layout(L, chi_cap, R);
+  tc_ctx *c = new tc_ctx();
+  c->device = device;
+  if (arena) {
+    if (arena_bytes < lo.total) {
+      delete c;
+      return fail("tc_ctx_create: arena too small");
+    }
+    if (((uintptr_t)arena & 255) != 0) {
+      delete c;
+      return fail("tc_ctx_create: arena must be 256-byte aligned");
+    }
+    c->arena = arena;
+  } else {
+    cudaError_t e = cudaMalloc(&c->arena, lo.total);
+    if (e != cudaSuccess) {
+      delete c;
+      return fail("tc_ctx_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+    }
+    c->own_arena = true;
+  }
+  c->arena_bytes = lo.total;
+  if (stream) {
+    c->stream = (cudaStream_t)stream;
+  } else {
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      if (c->own_arena) cudaFree(c->arena);
+      delete c;
+      return fail("tc_ctx_create: stream: %s", cudaGetErrorString(e));
+    }
+    c->own_stream = true;
+  }
+  char *base = (char *)c->arena;
+  TcDev &d = c->d;
+  d.L = L;
+  d.chi_cap = chi_cap;
+  d.R = R;
+  d.n2 = lo.n2;
+  d.nbmax = lo.nbmax;
+  d.ws_chains = lo.ws_chains;
+  d.site_stride = (size_t)chi_cap * 2 * chi_cap;
+  d.slot_stride = (size_t)lo.n2 * lo.n2;
+  d.B = (cplx *)(base + lo.B);
+  d.S = (double *)(base + lo.S);
+  d.chi = (int *)(base + lo.chi);
+  d.init_idx = (int8_t *)(base + lo.init_idx);
+  c->gates_dev = (cplx *)(base + lo.gates);
+  c->kick_dev = (cplx *)(base + lo.kick);
+  d.gates = c->gates_dev;
+  d.kick = c->kick_dev;
+  d.gates_diag = 0;
+  d.trunc_err = (double *)(base + lo.trunc_err);
+  d.flags = (int *)(base + lo.flags);
+  d.Cw = (cplx *)(base + lo.Cw);
+  d.Xw = (cplx *)(base + lo.Xw);
+  d.ww = (double *)(base + lo.ww);
+  d.perm = (int *)(base + lo.perm);
+  d.knew = (int *)(base + lo.knew);
+  d.renorm = (double *)(base + lo.renorm);
+  c->op_scratch = (cplx *)(base + lo.op);
+  c->E0 = (cplx *)(base + lo.E0);
+  c->E1 = (cplx *)(base + lo.E1);
+  c->Tt = (cplx *)(base + lo.Tt);
+  c->small_out = (double *)(base + lo.small_out);
+  d.mode = TC_TRUNC_REFERENCE;
+  d.cutoff = 1e-13;
+  d.chi_max = 0;
+  d.svd_min = 0.0;
+  d.trunc_cut = 0.0;
+  cudaMemsetAsync(d.flags, 0, 8 * sizeof(int), c->stream);
+  cudaMemsetAsync(d.trunc_err, 0, (size_t)R * (L + 1) * sizeof(double), c->stream);
+  cudaMemsetAsync(d.init_idx, 0, (size_t)R * L, c->stream);
+  // default state: |0...0>
+  tco::product_state_kernel<<<R, 64, 0, c->stream>>>(d);
+  g_launches.fetch_add(1);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    tc_ctx_destroy(c);
+    return fail("tc_ctx_create: init kernel: %s", cudaGetErrorString(e));
+  }
+  *out = c;
+  return 0;
+}
+
+int tc_ctx_destroy(tc_ctx *c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->rec) cudaFree(c->rec);
+  if (c->own_arena) cudaFree(c->arena);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int tc_sync(tc_ctx *c) {
+  CTX(c);
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int tc_ctx_info(tc_ctx *c, int *L, int *chi_cap, int *R, int *device) {
+  if (!c) return fail("null context");
+  if (L) *L = c->d.L;
+  if (chi_cap) *chi_cap = c->d.chi_cap;
+  if (R) *R = c->d.R;
+  if (device) *device = c->device;
+  return 0;
+}
+
+int tc_get_flags(tc_ctx *c, int32_t *out4) {
+  CTX(c);
+  CK(cudaMemcpyAsync(out4, c->d.flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ---- state ----------------------------------------------------------------------------------
+int tc_set_product_state(tc_ctx *c, const int8_t *idx_host) {
+  CTX(c);
+  const size_t n = (size_t)c->d.R * c->d.L;
+  for (size_t k = 0; k < n; ++k)
+    if (idx_host[k] != 0 && idx_host[k] != 1) return fail("tc_set_product_state: basis index must be 0 or 1");
+  CK(cudaMemcpyAsync(c->d.init_idx, idx_host, n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));  // idx_host may be pageable and reused by the caller
+  tco::product_state_kernel<<<c->d.R, 64, 0, c->stream>>>(c->d);
+  LAUNCHED();
+  return 0;
+}
+
+static int read_chi(tc_ctx *c, int r, std::vector<int> &chi) {
+  chi.resize(c->d.L + 1);
+  CK(cudaMemcpyAsync(chi.data(), c->d.chi + (size_t)r * (c->d.L + 1), chi.size() * sizeof(int),
+                     cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int tc_set_site(tc_ctx *c, int r, int site, const double *data_host, int chi_l, int chi_r) {
+  CTX(c);
+  const TcDev &d = c->d;
+  if (r < 0 || r >= d.R || site < 0 || site >= d.L) return fail("tc_set_site: index out of range");
+  if (chi_l < 1 || chi_r < 1 || chi_l > d.chi_cap || chi_r > d.chi_cap) return fail("tc_set_site: chi out of range");
+  cplx *B = d.B + ((size_t)r * d.L + site) * d.site_stride;
+  CK(cudaMemcpyAsync(B, data_host, (size_t)chi_l * 2 * chi_r * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
+  int dims[2] = {chi_l, chi_r};
+  CK(cudaMemcpyAsync(d.chi + (size_t)r * (d.L + 1) + site, dims, 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int tc_get_site(tc_ctx *c, int r, int site, double *out_host, int *chi_l, int *chi_r) {
+  CTX(c);
+  const TcDev &d = c->d;
+  if (r < 0 || r >= d.R || site < 0 || site >= d.L) return fail("tc_get_site: index out of range");
+  std::vector<int> chi;
+  if (read_chi(c, r, chi)) return 1;
+  if (chi_l) *chi_l = chi[site];
+  if (chi_r) *chi_r = chi[site + 1];
+  if (out_host) {
+    const cplx *B = d.B + ((size_t)r * d.L + site) * d.site_stride;
+    CK(cudaMemcpyAsync(out_host, B, (size_t)chi[site] * 2 * chi[site + 1] * sizeof(cplx), cudaMemcpyDeviceToHost,
+                       c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
+int tc_set_S(tc_ctx *c, int r, int bond, const double *S_host, int n) {
+  CTX(c);
+  const TcDev &d = c->d;
+  if (r < 0 || r >= d.R || bond < 0 || bond > d.L) return fail("tc_set_S: index out of range");
+  if (n < 1 || n > d.chi_cap) return fail("tc_set_S: n out of range");
+  CK(cudaMemcpyAsync(d.S + ((size_t)r * (d.L + 1) + bond) * d.chi_cap, S_host, n * sizeof(double),
+                     cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d.chi + (size_t)r * (d.L + 1) + bond, &n, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int tc_get_S(tc_ctx *c, int r, int bond, double *out_host, int *n) {
+  CTX(c);
+  const TcDev &d = c->d;
+  if (r < 0 || r >= d.R || bond < 0 || bond > d.L) return fail("tc_get_S: index out of range");
+  std::vector<int> chi;
+  if (read_chi(c, r, chi)) return 1;
+  if (n) *n = chi[bond];
+  if (out_host) {
+    CK(cudaMemcpyAsync(out_host, d.S + ((size_t)r * (d.L + 1) + bond) * d.chi_cap, chi[bond] * sizeof(double),
+                       cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
+int tc_get_chi(tc_ctx *c, int32_t *out_host) {
+  CTX(c);
+  CK(cudaMemcpyAsync(out_host, c->d.chi, (size_t)c->d.R * (c->d.L + 1) * sizeof(int), cudaMemcpyDeviceToHost,
+                     c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int tc_copy_chain(tc_ctx *dst, int r_dst, tc_ctx *src, int r_src) {
+  CTX(src);
+  if (!dst) return fail("null context");
+  if (dst->device != src->device) return fail("tc_copy_chain: contexts live on different devices");
+  if (dst->d.L != src->d.L) return fail("tc_copy_chain: chain lengths differ");
+  if (r_dst < 0 || r_dst >= dst->d.R || r_src < 0 || r_src >= src->d.R) return fail("tc_copy_chain: chain out of range");
+  std::vector<int> chi;
+  if (read_chi(src, r_src, chi)) return 1;
+  for (int v : chi)
+    if (v > dst->d.chi_cap) return fail("tc_copy_chain: destination chi_cap too small");
+  if (dst->stream != src->stream) CK(cudaStreamSynchronize(dst->stream));
+  tco::copy_chain_kernel<<<src->d.L + 1, 256, 0, src->stream>>>(dst->d, r_dst, src->d, r_src);
+  LAUNCHED();
+  if (dst->stream != src->stream) CK(cudaStreamSynchronize(src->stream));
+  return 0;
+}
+
+int tc_get_trunc_err(tc_ctx *c, double *out_host, int reset) {
+  CTX(c);
+  const TcDev &d = c->d;
+  std::vector<double> tmp((size_t)d.R * (d.L + 1));
+  CK(cudaMemcpyAsync(tmp.data(), d.trunc_err, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (reset) CK(cudaMemsetAsync(d.trunc_err, 0, tmp.size() * sizeof(double), c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int r = 0; r < d.R; ++r) {
+    double s = 0.0;
+    for (int b = 0; b <= d.L; ++b) s += tmp[(size_t)r * (d.L + 1) + b];
+    out_host[r] = s;
+  }
+  return 0;
+}
+
+// ---- model ----------------------------------------------------------------------------------
+int tc_set_model(tc_ctx *c, const double *gates_host, const double *kick_host) {
+  CTX(c);
+  const TcDev &d = c->d;
+  if (gates_host && d.L > 1) {
+    const size_t ng = (size_t)d.R * (d.L - 1);
+    c->d.gates_diag = gates_all_diagonal(gates_host, ng) ? 1 : 0;
+    CK(cudaMemcpyAsync(c->gates_dev, gates_host, ng * 16 * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
+  }
+  if (kick_host) CK(cudaMemcpyAsync(c->kick_dev, kick_host, (size_t)d.R * 4 * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (gates_host || d.L == 1) c->have_model = true;
+  return 0;
+}
+
+int tc_set_trunc(tc_ctx *c, int mode, double cutoff, int chi_max, double svd_min, double trunc_cut) {
+  if (!c) return fail("null context");
+  if (mode != TC_TRUNC_REFERENCE && mode != TC_TRUNC_TEBD) return fail("tc_set_trunc: unknown mode");
+  if (trunc_cut >= 1.0) return fail("tc_set_trunc: trunc_cut >= 1");
+  c->d.mode = mode;
+  c->d.cutoff = cutoff;
+  c->d.chi_max = chi_max;
+  c->d.svd_min = svd_min;
+  c->d.trunc_cut = trunc_cut;
+  return 0;
+}
+
+// ---- gates ----------------------------------------------------------------------------------
+int tc_apply_layer(tc_ctx *c, int parity, int kick_mode) {
+  CTX(c);
+  if (!c->have_model) return fail("tc_apply_layer: no model set");
+  if (parity != 0 && parity != 1) return fail("tc_apply_layer: parity must be 0 or 1");
+  return run_layer(c, parity, kick_mode);
+}
+
+int tc_apply_kick(tc_ctx *c) {
+  CTX(c);
+  return run_kick_all(c);
+}
+
+int tc_floquet_step(tc_ctx *c, int n_steps) {
+  CTX(c);
+  if (!c->have_model) return fail("tc_floquet_step: no model set");
+  for (int t = 0; t < n_steps; ++t)
+    if (run_period(c)) return 1;
+  return 0;
+}
+
+int tc_apply_two_site(tc_ctx *c, int r, int site, const double *gate_host) {
+  CTX(c);
+  const TcDev &d = c->d;
+  if (r < 0 || r >= d.R) return fail("tc_apply_two_site: chain out of range");
+  if (site < 0 || site + 1 >= d.L) return fail("tc_apply_two_site: site out of range");
+  CK(cudaMemcpyAsync(c->op_scratch, gate_host, 16 * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  const int diag = gates_all_diagonal(gate_host, 1) ? 1 : 0;
+  return run_bonds(c, site, 1, r, r + 1, 0, c->op_scratch, diag);
+}
+
+int tc_apply_one_site(tc_ctx *c, int r, int site, const double *op_host) {
+  CTX(c);
+  const TcDev &d = c->d;
+  if (r < 0 || r >= d.R || site < 0 || site >= d.L) return fail("tc_apply_one_site: index out of range");
+  CK(cudaMemcpyAsync(c->op_scratch + 16, op_host, 4 * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  tco::one_site_kernel<<<dim3(1, 1), 256, 0, c->stream>>>(d, r, site, c->op_scratch + 16);
+  LAUNCHED();
+  return 0;
+}
+
+// ---- observables ----------------------------------------------------------------------------
+int tc_measure_dev(tc_ctx *c, double *rdm_dev, double *ent_dev) {
+  CTX(c);
+  return measure_into(c, rdm_dev, nullptr, ent_dev, nullptr, nullptr);
+}
+
+static int ensure_rec(tc_ctx *c, size_t bytes) {
+  if (c->rec_bytes >= bytes) return 0;
+  if (c->rec) cudaFree(c->rec);
+  c->rec = nullptr;
+  c->rec_bytes = 0;
+  CK(cudaMalloc(&c->rec, bytes));
+  c->rec_bytes = bytes;
+  return 0;
+}
+
+int tc_measure(tc_ctx *c, double *rdm_host, double *ent_host) {
+  CTX(c);
+  const TcDev &d = c->d;
+  const size_t nr = (size_t)d.R * d.L * 4, ne = (size_t)d.R * (d.L > 1 ? d.L - 1 : 0);
+  if (ensure_rec(c, (nr + ne + 1) * sizeof(double))) return 1;
+  double *rd = (double *)c->rec, *ed = rd + nr;
+  if (measure_into(c, rdm_host ? rd : nullptr, nullptr, (ent_host && ne) ? ed : nullptr, nullptr, nullptr)) return 1;
+  if (rdm_host) CK(cudaMemcpyAsync(rdm_host, rd, nr * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (ent_host && ne) CK(cudaMemcpyAsync(ent_host, ed, ne * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+static int transfer(tc_ctx *bra, int rb, tc_ctx *ket, int rk, int lo, int hi, const cplx *op_lo, const cplx *op_hi,
+                    int init_mode, double *out_host) {
+  if (bra->d.chi_cap > ket->d.chi_cap) {
+    // scratch is taken from the ket context and sized chi_cap_ket^2; the bra may be larger
+    std::vector<int> chi;
+    if (read_chi(bra, rb, chi)) return 1;
+    for (int v : chi)
+      if (v > ket->d.chi_cap) return fail("tc_overlap: bra bond dimension exceeds the ket context's chi_cap");
+  }
+  if (bra->stream != ket->stream) CK(cudaStreamSynchronize(bra->stream));
+  tco::transfer_kernel<<<1, tco::NT, 0, ket->stream>>>(bra->d, rb, ket->d, rk, lo, hi, op_lo, op_hi, init_mode,
+                                                        ket->E0, ket->E1, ket->Tt, ket->small_out);
+  LAUNCHED();
+  CK(cudaMemcpyAsync(out_host, ket->small_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, ket->stream));
+  CK(cudaStreamSynchronize(ket->stream));
+  return 0;
+}
+
+int tc_overlap(tc_ctx *bra, int r_bra, tc_ctx *ket, int r_ket, double *out_host) {
+  CTX(ket);
+  if (!bra) return fail("null context");
+  if (bra->device != ket->device) return fail("tc_overlap: contexts live on different devices");
+  if (bra->d.L != ket->d.L) return fail("tc_overlap: chain lengths differ");
+  if (r_bra < 0 || r_bra >= bra->d.R || r_ket < 0 || r_ket >= ket->d.R) return fail("tc_overlap: chain out of range");
+  return transfer(bra, r_bra, ket, r_ket, 0, ket->d.L - 1, nullptr, nullptr, 0, out_host);
+}
+
+int tc_correlation(tc_ctx *c, int r, int i, int j, const double *op1_host, const double *op2_host, double *out_host) {
+  CTX(c);
+  const TcDev &d = c->d;
+  if (r < 0 || r >= d.R || i < 0 || j < 0 || i >= d.L || j >= d.L) return fail("tc_correlation: index out of range");
+  const double *lo_op = op1_host, *hi_op = op2_host;
+  int lo = i, hi = j;
+  if (i > j) {
+    lo = j;
+    hi = i;
+    lo_op = op2_host;
+    hi_op = op1_host;
+  }
+  CK(cudaMemcpyAsync(c->op_scratch + 20, lo_op, 4 * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->op_scratch + 24, hi_op, 4 * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  // for i == j the kernel multiplies op_lo op_hi, which must be op1 op2
+  if (i == j) return transfer(c, r, c, r, lo, hi, c->op_scratch + 20, c->op_scratch + 24, 1, out_host);
+  return transfer(c, r, c, r, lo, hi, c->op_scratch + 20, c->op_scratch + 24, 1, out_host);
+}
+
+// ---- fused time loop ------------------------------------------------------------------------
+int tc_floquet_run_dev(tc_ctx *c, int n_steps, int measure_every, int rec0, int measure_now, double *Z_dev,
+                       double *ent_dev, double *ov_dev, int32_t *chi_dev) {
+  CTX(c);
+  const TcDev &d = c->d;
+  if (n_steps > 0 && !c->have_model) return fail("tc_floquet_run_dev: no model set");
+  if (measure_every < 1) measure_every = 1;
+  const size_t zs = (size_t)d.R * d.L, es = (size_t)d.R * (d.L > 1 ? d.L - 1 : 0), os = (size_t)d.R * 2,
+               cs = (size_t)d.R * (d.L + 1);
+  auto rec = [&](int k) {
+    return measure_into(c, nullptr, Z_dev ? Z_dev + zs * k : nullptr, (ent_dev && es) ? ent_dev + es * k : nullptr,
+                        ov_dev ? ov_dev + os * k : nullptr, chi_dev ? chi_dev + cs * k : nullptr);
+  };
+  int k = rec0;
+  if (measure_now) {
+    if (rec(k)) return 1;
+    ++k;
+  }
+  for (int t = 0; t < n_steps; ++t) {
+    if (run_period(c)) return 1;
+    if (t % measure_every == 0) {
+      if (rec(k)) return 1;
+      ++k;
+    }
+  }
+  return 0;
+}
+
+int tc_floquet_run_host(tc_ctx *c, const double *gates_host, const double *kick_host, int n_steps, int measure_every,
+                        int measure_now, double *Z_host, double *ent_host, double *ov_host, int32_t *chi_host) {
+  CTX(c);
+  const TcDev &d = c->d;
+  if (gates_host || kick_host)
+    if (tc_set_model(c, gates_host, kick_host)) return 1;
+  if (measure_every < 1) measure_every = 1;
+  const int n_rec = (measure_now ? 1 : 0) + (n_steps > 0 ? (n_steps - 1) / measure_every + 1 : 0);
+  const size_t zs = (size_t)d.R * d.L, es = (size_t)d.R * (d.L > 1 ? d.L - 1 : 0), os = (size_t)d.R * 2,
+               cs = (size_t)d.R * (d.L + 1);
+  const size_t nz = Z_host ? zs * n_rec : 0, ne = ent_host ? es * n_rec : 0, no = ov_host ? os * n_rec : 0,
+               nc = chi_host ? cs * n_rec : 0;
+  if (ensure_rec(c, (nz + ne + no + 1) * sizeof(double) + nc * sizeof(int32_t))) return 1;
+  double *Zd = (double *)c->rec, *Ed = Zd + nz, *Od = Ed + ne;
+  int32_t *Cd = (int32_t *)(Od + no);
+  if (tc_floquet_run_dev(c, n_steps, measure_every, 0, measure_now, nz ? Zd : nullptr, ne ? Ed : nullptr,
+                         no ? Od : nullptr, nc ? Cd : nullptr))
+    return 1;
+  if (nz) CK(cudaMemcpyAsync(Z_host, Zd, nz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (ne) CK(cudaMemcpyAsync(ent_host, Ed, ne * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (no) CK(cudaMemcpyAsync(ov_host, Od, no * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (nc) CK(cudaMemcpyAsync(chi_host, Cd, nc * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+// ---- diagnostics ----------------------------------------------------------------------------
+int tc_dbg_get(tc_ctx *c, int which, int r, int jb, void *out_host, size_t bytes) {
+  CTX(c);
+  const TcDev &d = c->d;
+  if (r < 0 || r >= d.ws_chains || jb < 0 || jb >= d.nbmax) return fail("tc_dbg_get: slot out of range");
+  const size_t slot = (size_t)r * d.nbmax + jb;
+  const void *src = nullptr;
+  size_t maxb = 0;
+  switch (which) {
+    case TC_DBG_C: src = d.Cw + slot * d.slot_stride; maxb = d.slot_stride * sizeof(cplx); break;
+    case TC_DBG_X: src = d.Xw + slot * d.slot_stride; maxb = d.slot_stride * sizeof(cplx); break;
+    case TC_DBG_W: src = d.ww + slot * d.n2; maxb = d.n2 * sizeof(double); break;
+    case TC_DBG_PERM: src = d.perm + slot * d.n2; maxb = d.n2 * sizeof(int); break;
+    default: return fail("tc_dbg_get: unknown buffer");
+  }
+  if (bytes > maxb) return fail("tc_dbg_get: too many bytes");
+  CK(cudaMemcpyAsync(out_host, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int tc_probe_fp64(int device, int use_dmma, double *gflops_out) {
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  double *out;
+  CK(cudaMalloc(&out, 8));
+  const int iters = 20000, blocks = prop.multiProcessorCount * 8;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {
+    CK(cudaEventRecord(e0));
+    if (use_dmma)
+      probe_dmma_kernel<<<blocks, 256>>>(out, iters);
+    else
+      probe_fma_kernel<<<blocks, 256>>>(out, iters);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  g_launches.fetch_add(4);
+  // per thread per iteration: 8 FMA (2 flop) or, per warp, 8 DMMA m8n8k4 (512 flop)
+  const double flop = use_dmma ? (double)blocks * 8 * iters * 8 * 512.0 : (double)blocks * 256 * iters * 8 * 2.0;
+  *gflops_out = flop / (best * 1e-3) * 1e-9;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  return 0;
+}
+
+}  // extern "C"

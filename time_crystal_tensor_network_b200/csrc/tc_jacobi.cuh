@@ -1,0 +1,239 @@
+// tc_jacobi.cuh -- batched truncated SVD of the two-site tensor theta (complex FP64) by one-sided
+// Jacobi (Hestenes) on the ROWS of theta, one CTA per matrix, followed by sort + truncation +
+// renormalisation in-kernel.
+//
+// Only right singular vectors are needed by the inverse-free TEBD update (B_{i+1} = V_k^H,
+// B_i = C V_k), so the rotations act from the left:  J^H theta = Sigma V^H.  When the
+// rows of theta are mutually orthogonal, row k IS sigma_k v_k^H: no rotation accumulation, no U,
+// and the normalised rows drop straight into the (k, p1, chi_r) layout of site i+1.  One-sided
+// Jacobi keeps high relative accuracy for the small singular values the reference retains
+// (sigma > 1e-13, kicked_ising.py:186 -> TeNPy apply_local_op default cutoff).
+#pragma once
+#include "tc_common.cuh"
+
+namespace tcj {
+constexpr int NT = 256;
+constexpr int MAX_SWEEPS = 48;
+constexpr double DEAD_REL2 = 1e-30;  // rows with |x|^2 < DEAD_REL2 * |theta|_F^2 are numerically zero
+
+// round-robin tournament (circle method): pair k of round r among M players (M even)
+__device__ __forceinline__ void rr_pair(int M, int r, int k, int &i, int &j) {
+  const int m1 = M - 1;
+  if (k == 0) {
+    i = m1;
+    j = r;
+  } else {
+    i = r + k;
+    if (i >= m1) i -= m1;
+    j = r - k;
+    if (j < 0) j += m1;
+  }
+  if (i > j) {
+    int t = i;
+    i = j;
+    j = t;
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// v1: warp per row pair, rows streamed from L1/L2.  dynamic smem: n2 doubles (row norms^2)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) jacobi_rows_kernel(TcDev d, LayerArgs a) {
+  Bond b;
+  if (!get_bond(d, a, blockIdx.x, blockIdx.y, b)) return;
+  const int M = b.M, N = b.N;
+  cplx *X = d.Xw + b.slot * d.slot_stride;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *nrm2 = reinterpret_cast<double *>(smem_raw);
+  __shared__ double red[32];
+  __shared__ int s_rot;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = NT / 32;
+  const double tol = 2.0 * sqrt((double)N) * 2.220446049250313e-16;
+  const double tol2 = tol * tol;
+
+  double dead = 0.0;
+  int sweep = 0;
+  for (; sweep < MAX_SWEEPS; ++sweep) {
+    // fresh row norms at the start of every sweep
+    for (int r = warp; r < M; r += NW) {
+      const cplx *row = X + (size_t)r * N;
+      double s = 0.0;
+      for (int c = lane; c < N; c += 32) s += cabs2(row[c]);
+      s = warp_sum(s);
+      if (lane == 0) nrm2[r] = s;
+    }
+    if (tid == 0) s_rot = 0;
+    __syncthreads();
+    if (sweep == 0) {
+      double p = 0.0;
+      for (int r = tid; r < M; r += NT) p += nrm2[r];
+      dead = DEAD_REL2 * block_sum(p, red);
+    }
+    int nrot = 0;
+    for (int r = 0; r < M - 1; ++r) {
+      for (int k = warp; k < M / 2; k += NW) {
+        int i, j;
+        rr_pair(M, r, k, i, j);
+        const double ai = nrm2[i], aj = nrm2[j];
+        if (ai <= dead || aj <= dead) continue;
+        cplx *xi = X + (size_t)i * N, *xj = X + (size_t)j * N;
+        double gr = 0.0, gi = 0.0;  // g = sum x_i conj(x_j)
+        for (int c = lane; c < N; c += 32) {
+          const cplx u = xi[c], v = xj[c];
+          gr = fma(u.x, v.x, gr);
+          gr = fma(u.y, v.y, gr);
+          gi = fma(u.y, v.x, gi);
+          gi = fma(-u.x, v.y, gi);
+        }
+        gr = warp_sum(gr);
+        gi = warp_sum(gi);
+        const double g2 = gr * gr + gi * gi;
+        if (!(g2 > tol2 * ai * aj)) continue;
+        const double ga = sqrt(g2);
+        const double zeta = (aj - ai) / (2.0 * ga);
+        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double cs = 1.0 / sqrt(1.0 + t * t);
+        const double sn = cs * t;
+        const double er = gr / ga, ei = gi / ga;  // e = g / |g|
+        const double sr = sn * er, si = sn * ei;  // s e
+        // x_i' = c x_i - (s e) x_j ;  x_j' = conj(s e) x_i + c x_j
+        for (int c = lane; c < N; c += 32) {
+          const cplx u = xi[c], v = xj[c];
+          cplx un, vn;
+          un.x = cs * u.x - (sr * v.x - si * v.y);
+          un.y = cs * u.y - (sr * v.y + si * v.x);
+          vn.x = cs * v.x + (sr * u.x + si * u.y);
+          vn.y = cs * v.y + (sr * u.y - si * u.x);
+          xi[c] = un;
+          xj[c] = vn;
+        }
+        if (lane == 0) {
+          nrm2[i] = ai - t * ga;
+          nrm2[j] = aj + t * ga;
+        }
+        ++nrot;
+      }
+      __syncthreads();
+    }
+    if (lane == 0 && nrot) atomicAdd(&s_rot, nrot);
+    __syncthreads();
+    const int tot = s_rot;
+    __syncthreads();
+    if (tot == 0) break;
+  }
+  if (tid == 0) {
+    if (sweep >= MAX_SWEEPS) atomicAdd(&d.flags[1], 1);
+    atomicMax(&d.flags[2], sweep + 1);
+  }
+  // singular values = final row norms
+  double *w = d.ww + b.slot * d.n2;
+  for (int r = warp; r < M; r += NW) {
+    const cplx *row = X + (size_t)r * N;
+    double s = 0.0;
+    for (int c = lane; c < N; c += 32) s += cabs2(row[c]);
+    s = warp_sum(s);
+    if (lane == 0) w[r] = sqrt(s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sort + truncation + renormalisation + write-back of S_{i+1}, chi_{i+1} and B_{i+1} = V_k^H.
+// Truncation rules: mode 0 = TeNPy apply_local_op default (keep sigma > cutoff, absolute);
+// mode 1 = TeNPy truncate() (chi_max, svd_min, trunc_cut on the normalised spectrum); SURVEY A.2.3/A.2.5.
+// dynamic smem: n2 doubles (sorted values)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT) finalize_kernel(TcDev d, LayerArgs a) {
+  Bond b;
+  if (!get_bond(d, a, blockIdx.x, blockIdx.y, b)) return;
+  const int M = b.M, N = b.N;
+  const cplx *X = d.Xw + b.slot * d.slot_stride;
+  const double *w = d.ww + b.slot * d.n2;
+  int *perm = d.perm + b.slot * d.n2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *sorted = reinterpret_cast<double *>(smem_raw);
+  __shared__ int s_k;
+  __shared__ double s_renorm;
+  const int tid = threadIdx.x;
+
+  // descending rank sort (stable)
+  for (int t = tid; t < M; t += NT) {
+    const double wt = w[t];
+    int rank = 0;
+    for (int j = 0; j < M; ++j) {
+      const double wj = w[j];
+      rank += (wj > wt) || (wj == wt && j < t);
+    }
+    perm[rank] = t;
+    sorted[rank] = wt;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double tot2 = 0.0;
+    for (int j = M - 1; j >= 0; --j) tot2 += sorted[j] * sorted[j];
+    const double tot = sqrt(tot2);
+    int kk;
+    if (d.mode == 0) {
+      kk = 0;
+      while (kk < M && sorted[kk] > d.cutoff) ++kk;
+    } else {
+      kk = M;
+      if (d.chi_max > 0 && d.chi_max < kk) kk = d.chi_max;
+      int ksvd = 0;
+      const double smin = d.svd_min * tot;  // s / tot > svd_min
+      while (ksvd < M && sorted[ksvd] > smin) ++ksvd;
+      if (ksvd >= 1 && ksvd < kk) kk = ksvd;
+      if (d.trunc_cut > 0.0) {
+        const double lim = d.trunc_cut * d.trunc_cut * tot2;
+        double c = 0.0;
+        int first_good = -1;
+        for (int j = M - 1; j >= 0; --j) {
+          c += sorted[j] * sorted[j];
+          if (c > lim) {
+            first_good = j;
+            break;
+          }
+        }
+        if (first_good >= 0 && first_good + 1 < kk) kk = first_good + 1;
+      }
+    }
+    if (kk < 1) kk = 1;
+    const int lim_rank = M < N ? M : N;  // rank of theta cannot exceed min(M, N)
+    if (kk > lim_rank) kk = lim_rank;
+    if (kk > d.chi_cap) {
+      kk = d.chi_cap;
+      atomicAdd(&d.flags[0], 1);
+    }
+    double kept2 = 0.0;
+    for (int j = kk - 1; j >= 0; --j) kept2 += sorted[j] * sorted[j];
+    double ren = sqrt(kept2);
+    if (!(ren > 0.0)) ren = 1.0;
+    s_renorm = ren;
+    s_k = kk;
+    d.knew[b.slot] = kk;
+    d.renorm[b.slot] = ren;
+    d.chi[(size_t)b.r * (d.L + 1) + b.i + 1] = kk;
+    double disc = 0.0;
+    for (int j = M - 1; j >= kk; --j) disc += sorted[j] * sorted[j];
+    if (tot2 > 0.0) d.trunc_err[(size_t)b.r * (d.L + 1) + b.i + 1] += disc / tot2;
+  }
+  __syncthreads();
+  const int kk = s_k;
+  const double inv = 1.0 / s_renorm;
+  double *Sout = S_ptr(d, b.r, b.i + 1);
+  for (int j = tid; j < kk; j += NT) Sout[j] = sorted[j] * inv;
+  // B_{i+1}[k][p1][b] = row perm[k] of X / sigma_k
+  cplx *Bn = site_ptr(d, b.r, b.i + 1);
+  for (int e = tid; e < kk * N; e += NT) {
+    const int k = e / N, c = e - k * N;
+    const double s = sorted[k];
+    const cplx v = X[(size_t)perm[k] * N + c];
+    Bn[e] = s > 0.0 ? cscale(v, 1.0 / s) : cmake(0.0, 0.0);
+  }
+}
+}  // namespace tcj

@@ -1,0 +1,237 @@
+// tc_observe.cuh -- state set-up, single-site gates and the observable kernels (HBM-bound passes).
+//
+// Every site tensor is kept in right-canonical 'B' form with the Schmidt values of the bond on its
+// left in S, so theta_i = S_i B_i and
+//   <O_i>     = sum_{a,b,p,q} S_a^2 conj(B[a,p,b]) O[p,q] B[a,q,b]        (MPS.expectation_value, observables.py:62)
+//   S_ent(b)  = -sum_k s_k^2 ln s_k^2, s_k^2 > 1e-30                      (MPS.entanglement_entropy, tensor_utils.py:180)
+//   <psi0|psi> with psi0 a product state = B_0[idx_0] B_1[idx_1] ...      (MPS.overlap, observables.py:25)
+#pragma once
+#include "tc_common.cuh"
+
+namespace tco {
+constexpr int NT = 256;
+
+// MPS.from_product_state (tensor_utils.py:60): chi = 1 everywhere, one-hot tensors, S = 1.
+__global__ void product_state_kernel(TcDev d) {
+  const int r = blockIdx.x;
+  for (int i = threadIdx.x; i <= d.L; i += blockDim.x) {
+    d.chi[(size_t)r * (d.L + 1) + i] = 1;
+    S_ptr(d, r, i)[0] = 1.0;
+    d.trunc_err[(size_t)r * (d.L + 1) + i] = 0.0;
+    if (i < d.L) {
+      cplx *B = site_ptr(d, r, i);
+      const int idx = d.init_idx[(size_t)r * d.L + i];
+      B[0] = cmake(idx == 0 ? 1.0 : 0.0, 0.0);
+      B[1] = cmake(idx == 1 ? 1.0 : 0.0, 0.0);
+    }
+  }
+}
+
+// single-site operator on the physical leg: B[a,p,b] <- sum_q op[p,q] B[a,q,b]
+// (MPS.apply_local_op one-site, unitary=True: no re-canonicalisation; kicked_ising.py:206).
+// grid (L or 1, R or 1); op_fixed == nullptr -> the model's kick of chain r
+__global__ void one_site_kernel(TcDev d, int r0, int site0, const cplx *op_fixed) {
+  const int r = r0 + blockIdx.y, site = site0 + blockIdx.x;
+  const cplx *op = op_fixed ? op_fixed : d.kick + (size_t)r * 4;
+  const cplx o00 = op[0], o01 = op[1], o10 = op[2], o11 = op[3];
+  const int *c = d.chi + (size_t)r * (d.L + 1);
+  const int chiL = c[site], chiR = c[site + 1];
+  cplx *B = site_ptr(d, r, site);
+  for (int e = threadIdx.x; e < chiL * chiR; e += blockDim.x) {
+    const int a = e / chiR, b = e - a * chiR;
+    cplx *p0 = B + (size_t)(2 * a) * chiR + b, *p1 = p0 + chiR;
+    const cplx x0 = *p0, x1 = *p1;
+    cplx y0 = cmul(o00, x0), y1 = cmul(o10, x0);
+    cfma(y0, o01, x1);
+    cfma(y1, o11, x1);
+    *p0 = y0;
+    *p1 = y1;
+  }
+}
+
+// one CTA per (site, chain): single-site reduced density matrix, <Z>, and the entropy of the bond
+// to the right of the site.  rdm[R][L][4] = (rho00, rho11, Re rho01, Im rho01), rho_pq = <p|rho|q>.
+// Output rows are indexed by the chain's position in the launch (r - r0) plus out_r0.
+__global__ void __launch_bounds__(NT) measure_kernel(TcDev d, double *rdm, double *Z, double *ent) {
+  const int site = blockIdx.x, r = blockIdx.y;
+  const int *c = d.chi + (size_t)r * (d.L + 1);
+  const int chiL = c[site], chiR = c[site + 1];
+  const cplx *B = site_ptr(d, r, site);
+  const double *S = S_ptr(d, r, site);
+  __shared__ double red[32];
+  double r00 = 0.0, r11 = 0.0, re01 = 0.0, im01 = 0.0;
+  for (int e = threadIdx.x; e < chiL * chiR; e += NT) {
+    const int a = e / chiR, b = e - a * chiR;
+    const double s2 = S[a] * S[a];
+    const cplx x0 = B[(size_t)(2 * a) * chiR + b], x1 = B[(size_t)(2 * a + 1) * chiR + b];
+    r00 = fma(s2, cabs2(x0), r00);
+    r11 = fma(s2, cabs2(x1), r11);
+    // rho01 = sum theta[a,0,b] conj(theta[a,1,b])
+    re01 = fma(s2, x0.x * x1.x + x0.y * x1.y, re01);
+    im01 = fma(s2, x0.y * x1.x - x0.x * x1.y, im01);
+  }
+  r00 = block_sum(r00, red);
+  r11 = block_sum(r11, red);
+  if (rdm) {
+    re01 = block_sum(re01, red);
+    im01 = block_sum(im01, red);
+  }
+  if (threadIdx.x == 0) {
+    const size_t o = (size_t)r * d.L + site;
+    if (rdm) {
+      rdm[o * 4 + 0] = r00;
+      rdm[o * 4 + 1] = r11;
+      rdm[o * 4 + 2] = re01;
+      rdm[o * 4 + 3] = im01;
+    }
+    if (Z) Z[o] = r00 - r11;
+  }
+  if (ent && site < d.L - 1) {
+    const double *Sr = S_ptr(d, r, site + 1);
+    double h = 0.0;
+    for (int k = threadIdx.x; k < chiR; k += NT) {
+      const double p = Sr[k] * Sr[k];
+      if (p > 1e-30) h -= p * log(p);
+    }
+    h = block_sum(h, red);
+    if (threadIdx.x == 0) ent[(size_t)r * (d.L - 1) + site] = h;
+  }
+}
+
+// <psi0|psi> for the product state psi0 given to tc_set_product_state: one CTA per chain, a chain
+// of vector-matrix products v <- v B_i[:, idx_i, :].  dynamic smem: 2 * chi_cap cplx.
+__global__ void __launch_bounds__(NT) overlap_product_kernel(TcDev d, double *ov) {
+  const int r = blockIdx.x;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx *v = reinterpret_cast<cplx *>(smem_raw);
+  cplx *vn = v + d.chi_cap;
+  const int *c = d.chi + (size_t)r * (d.L + 1);
+  if (threadIdx.x == 0) v[0] = cmake(1.0, 0.0);
+  __syncthreads();
+  for (int i = 0; i < d.L; ++i) {
+    const int chiL = c[i], chiR = c[i + 1];
+    const int idx = d.init_idx[(size_t)r * d.L + i];
+    const cplx *B = site_ptr(d, r, i) + (size_t)idx * chiR;
+    for (int b = threadIdx.x; b < chiR; b += NT) {
+      cplx acc = cmake(0.0, 0.0);
+      for (int a2 = 0; a2 < chiL; ++a2) cfma(acc, v[a2], B[(size_t)(2 * a2) * chiR + b]);
+      vn[b] = acc;
+    }
+    __syncthreads();
+    cplx *t = v;
+    v = vn;
+    vn = t;
+  }
+  if (threadIdx.x == 0) {
+    ov[(size_t)r * 2 + 0] = v[0].x;
+    ov[(size_t)r * 2 + 1] = v[0].y;
+  }
+}
+
+__global__ void chi_record_kernel(TcDev d, int32_t *out) {
+  const size_t n = (size_t)d.R * (d.L + 1);
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x)
+    out[e] = d.chi[e];
+}
+
+// General transfer-matrix contraction between chain ra of context da (bra, conjugated) and chain rb
+// of context db (ket) over sites lo..hi, with optional single-site operators at lo and hi:
+//   E'[a',b'] = sum_{a,b,p,q} conj(A[a,p,a']) O[p,q] E[a,b] K[b,q,b']
+// init_mode 0: E = [[1]] (overlap from site 0);  1: E = diag(S_lo^2) of the ket (correlators in one
+// state, whose left environment in canonical form is the squared Schmidt spectrum).
+// Result = trace(E) after site hi.  One CTA; E0/E1: chi_cap_a*chi_cap_b cplx, T: chi_cap_a*2*chi_cap_b.
+__global__ void __launch_bounds__(NT) transfer_kernel(TcDev da, int ra, TcDev db, int rb, int lo, int hi,
+                                                      const cplx *op_lo, const cplx *op_hi, int init_mode,
+                                                      cplx *E0, cplx *E1, cplx *T, double *out) {
+  const int tid = threadIdx.x;
+  const int *ca = da.chi + (size_t)ra * (da.L + 1), *cb = db.chi + (size_t)rb * (db.L + 1);
+  cplx *E = E0, *En = E1;
+  {
+    const int na = ca[lo], nb = cb[lo];
+    const double *S = S_ptr(db, rb, lo);
+    for (int e = tid; e < na * nb; e += NT) {
+      const int x = e / nb, y = e - x * nb;
+      double v = 0.0;
+      if (x == y) v = init_mode == 0 ? 1.0 : S[x] * S[x];
+      E[e] = cmake(v, 0.0);
+    }
+  }
+  __syncthreads();
+  for (int i = lo; i <= hi; ++i) {
+    const int na = ca[i], nb = cb[i], na2 = ca[i + 1], nb2 = cb[i + 1];
+    const cplx *A = site_ptr(da, ra, i), *K = site_ptr(db, rb, i);
+    const cplx *op = (i == lo && op_lo) ? op_lo : ((i == hi && op_hi) ? op_hi : nullptr);
+    cplx o00 = cmake(1, 0), o01 = cmake(0, 0), o10 = cmake(0, 0), o11 = cmake(1, 0);
+    if (op) {
+      o00 = op[0];
+      o01 = op[1];
+      o10 = op[2];
+      o11 = op[3];
+      if (i == lo && i == hi && op_lo && op_hi) {  // both operators on one site: O = op_lo op_hi
+        const cplx h00 = op_hi[0], h01 = op_hi[1], h10 = op_hi[2], h11 = op_hi[3];
+        const cplx l00 = op_lo[0], l01 = op_lo[1], l10 = op_lo[2], l11 = op_lo[3];
+        o00 = cadd(cmul(l00, h00), cmul(l01, h10));
+        o01 = cadd(cmul(l00, h01), cmul(l01, h11));
+        o10 = cadd(cmul(l10, h00), cmul(l11, h10));
+        o11 = cadd(cmul(l10, h01), cmul(l11, h11));
+      }
+    }
+    // T[a][p][b'] = sum_q O[p,q] sum_b E[a,b] K[b,q,b']
+    for (int e = tid; e < na * nb2; e += NT) {
+      const int x = e / nb2, y = e - x * nb2;
+      cplx t0 = cmake(0, 0), t1 = cmake(0, 0);
+      for (int b = 0; b < nb; ++b) {
+        const cplx ev = E[x * nb + b];
+        cfma(t0, ev, K[(size_t)(2 * b) * nb2 + y]);
+        cfma(t1, ev, K[(size_t)(2 * b + 1) * nb2 + y]);
+      }
+      cplx u0 = cmul(o00, t0), u1 = cmul(o10, t0);
+      cfma(u0, o01, t1);
+      cfma(u1, o11, t1);
+      T[(size_t)(2 * x) * nb2 + y] = u0;
+      T[(size_t)(2 * x + 1) * nb2 + y] = u1;
+    }
+    __syncthreads();
+    // E'[a'][b'] = sum_{a,p} conj(A[a,p,a']) T[a,p,b']
+    for (int e = tid; e < na2 * nb2; e += NT) {
+      const int x = e / nb2, y = e - x * nb2;
+      cplx acc = cmake(0, 0);
+      for (int ap = 0; ap < 2 * na; ++ap) cfmac(acc, A[(size_t)ap * na2 + x], T[(size_t)ap * nb2 + y]);
+      En[e] = acc;
+    }
+    __syncthreads();
+    cplx *t = E;
+    E = En;
+    En = t;
+  }
+  if (tid == 0) {
+    const int na = ca[hi + 1], nb = cb[hi + 1];
+    const int n = na < nb ? na : nb;
+    cplx tr = cmake(0, 0);
+    for (int k = 0; k < n; ++k) tr = cadd(tr, E[k * nb + k]);
+    out[0] = tr.x;
+    out[1] = tr.y;
+  }
+}
+
+// copy chain rs of src into chain rd of dst (compact site layout is chi_cap independent).
+__global__ void copy_chain_kernel(TcDev dst, int rd, TcDev src, int rs) {
+  const int site = blockIdx.x;  // 0..L (L = the last bond only)
+  const int *c = src.chi + (size_t)rs * (src.L + 1);
+  const int n = c[site];
+  if (threadIdx.x == 0) {
+    dst.chi[(size_t)rd * (dst.L + 1) + site] = n;
+    dst.trunc_err[(size_t)rd * (dst.L + 1) + site] = src.trunc_err[(size_t)rs * (src.L + 1) + site];
+    if (site < src.L) dst.init_idx[(size_t)rd * dst.L + site] = src.init_idx[(size_t)rs * src.L + site];
+  }
+  const double *Ss = S_ptr(src, rs, site);
+  double *Sd = S_ptr(dst, rd, site);
+  for (int k = threadIdx.x; k < n; k += blockDim.x) Sd[k] = Ss[k];
+  if (site < src.L) {
+    const int tot = n * 2 * c[site + 1];
+    const cplx *Bs = site_ptr(src, rs, site);
+    cplx *Bd = site_ptr(dst, rd, site);
+    for (int e = threadIdx.x; e < tot; e += blockDim.x) Bd[e] = Bs[e];
+  }
+}
+}  // namespace tco
