@@ -1,0 +1,340 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path: disorder-averaged Floquet steps/sec at L=32, chi=128, FP64.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...        # CPU arm: the oracle port on the box's host cores
+
+One "step" = one Floquet period (62 two-site updates with their SVDs + 32 kicks, the reference's
+sequence, src/models/kicked_ising.py:100-160) of every chain of the ensemble.  Weak scaling: every
+GPU evolves --chains independent disorder realisations (32 per GPU = 256 on 8 GPUs, BASELINE config).
+Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'disorder-avg Floquet steps/sec (L=32, chi=128, FP64)'
+UNIT = 'chain-steps/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=4)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--chains', type=int, default=32, help='chains per GPU')
+    ap.add_argument('--L', type=int, default=32)
+    ap.add_argument('--chi', type=int, default=128)
+    ap.add_argument('--eps', type=float, default=0.1)
+    ap.add_argument('--prep-eps', type=float, default=0.3, help='kick imperfection used to entangle the state')
+    ap.add_argument('--prep-max', type=int, default=40, help='max preparation periods')
+    ap.add_argument('--cpu-periods', type=int, default=2)
+    ap.add_argument('--no-cpu', action='store_true')
+    return ap.parse_args()
+
+
+WORK = dict(J=1.0, tau=1.0, W=0.3, svd_min=1e-12, trunc_cut=1e-7, state='neel', seed0=1000)
+
+
+def workload_name(a):
+    return (f'L{a.L}_chi{a.chi}_R{a.chains}perGPU_neel_W{WORK["W"]}_eps{a.eps}_tebd_svdmin1e-12_trunccut1e-7')
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic work: per update with theta m x n (m >= n), inner dim k, kept chi'
+# ------------------------------------------------------------------------------------------------
+def update_flops(chi_row):
+    """chi_row: int [L+1] bond dimensions.  Returns (F_theta, F_svd, F_B) summed over the 2(L-1) updates
+    of one period (every bond is updated twice)."""
+    ft = fs = fb = 0.0
+    L = len(chi_row) - 1
+    for i in range(L - 1):
+        cl, cm, cr = int(chi_row[i]), int(chi_row[i + 1]), int(chi_row[i + 2])
+        M, N = 2 * cl, 2 * cr
+        m, n = max(M, N), min(M, N)
+        ft += 8.0 * M * cm * N
+        fs += 4.0 * (4.0 * m * m * n + 8.0 * m * n * n + 9.0 * n ** 3)
+        fb += 8.0 * M * N * cm
+    return 2 * ft, 2 * fs, 2 * fb
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '200', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace('.', '').isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (NumPy/LAPACK restatement of the reference's TeNPy path)
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(task):
+    """Prepare one chain on the CPU (oracle O2, TEBD truncation) and time `n_timed` periods."""
+    seed, L, chi, eps, prep_eps, prep_max, n_warm, n_timed, threads = task
+    try:
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=threads)
+    except Exception:
+        limiter = None
+    from oracle import tebd_ref
+    h = tebd_ref.disorder_fields(L, WORK['W'], seed)
+    trunc = dict(chi_max=chi, svd_min=WORK['svd_min'], trunc_cut=WORK['trunc_cut'])
+    kick_p, gates = tebd_ref.make_gates(L, WORK['J'], h, WORK['tau'], prep_eps)
+    kick, _ = tebd_ref.make_gates(L, WORK['J'], h, WORK['tau'], eps)
+    psi = tebd_ref.product_state(L, 'neel', 1)
+    n_prep = 0
+    while n_prep < prep_max and min(psi.chi[L // 2 - 2:L // 2 + 2] or [chi]) < chi:
+        psi, _ = tebd_ref.floquet_step(psi, kick_p, gates, mode='tebd', trunc=trunc)
+        n_prep += 1
+    for _ in range(n_warm):
+        psi, _ = tebd_ref.floquet_step(psi, kick, gates, mode='tebd', trunc=trunc)
+    t0 = time.perf_counter()
+    for _ in range(n_timed):
+        psi, _ = tebd_ref.floquet_step(psi, kick, gates, mode='tebd', trunc=trunc)
+    dt = time.perf_counter() - t0
+    del limiter
+    return dt, n_prep, max(psi.chi)
+
+
+def cpu_ensemble_rate(a, n_warm, n_timed, procs=None):
+    """Best-case CPU throughput for independent chains: one single-threaded process per core."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    procs = procs or cores
+    tasks = [(WORK['seed0'] + r, a.L, a.chi, a.eps, a.prep_eps, a.prep_max, n_warm, n_timed, 1) for r in range(procs)]
+    t0 = time.perf_counter()
+    with mp.get_context('fork').Pool(procs) as pool:
+        res = pool.map(_cpu_worker, tasks)
+    wall = time.perf_counter() - t0
+    slowest = max(r[0] for r in res)
+    return {'value': procs * n_timed / slowest, 'cores': procs, 'ms_per_step': slowest / n_timed * 1e3,
+            'prep_periods': [r[1] for r in res], 'chi_max': max(r[2] for r in res), 'wall_s': wall}
+
+
+def run_reference(a):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    r = cpu_ensemble_rate(a, a.warmup if a.warmup < 2 else 1, max(1, min(a.steps, 3)))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': a.gpus,
+        'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'complex128 (f64)', 'data': 'synthetic',
+        'config': {'workload': workload_name(a), 'note': 'CPU arm: oracle port of the reference TEBD/TeNPy path '
+                   '(TeNPy itself is not installable here); one single-threaded process per host core, one chain each'},
+        'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
+                         'sample': f"{r['cores']} chains x {max(1, min(a.steps, 3))} periods at chi_max={r['chi_max']} "
+                                   f"after {max(r['prep_periods'])} preparation periods"},
+        'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from time_crystal_tensor_network_b200 import engine as eng
+    from time_crystal_tensor_network_b200.sharding import gather_records
+
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    rank = int(os.environ.get('RANK', 0))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local}'))
+    R = a.chains
+    L = a.L
+    seeds = [WORK['seed0'] + rank * R + r for r in range(R)]
+    hs = np.array([eng.disorder_fields(L, WORK['W'], s) for s in seeds])
+
+    ens = eng.FloquetEnsemble(L, WORK['J'], WORK['tau'], hs, epsilon=a.prep_eps, chi_max=a.chi, mode='tebd',
+                              svd_min=WORK['svd_min'], trunc_cut=WORK['trunc_cut'], state=WORK['state'], device=local)
+    ctx = ens.ctx
+    # ---- state preparation (untimed): entangle until the central bonds sit at chi_max
+    n_prep = 0
+    t_prep = time.perf_counter()
+    while n_prep < a.prep_max:
+        chi = ctx.chi()
+        if chi[:, L // 2 - 2:L // 2 + 3].min() >= min(a.chi, 2 ** (L // 2)):
+            break
+        ctx.floquet_step(1)
+        n_prep += 1
+    ctx.sync()
+    t_prep = time.perf_counter() - t_prep
+    kick = np.ascontiguousarray(np.broadcast_to(eng.kick_matrix(a.eps), (R, 2, 2)))
+    ctx.set_model(ens.gates, kick)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: W warm-up steps, then exactly K steps
+    # L2 note: one step streams the whole 2.1 GB (R=32) state plus 2 x 1 MiB workspaces per update
+    # through the 126 MB L2, i.e. inputs are far larger than L2; no explicit flush is needed.
+    for _ in range(a.warmup):
+        ctx.floquet_step(1)
+    barrier()
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = eng.launch_count()
+    ctx.profile(True)
+    ctx.profile_read(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with torch.cuda.stream(ctx.stream):
+        e0.record(ctx.stream)
+        ctx.floquet_step(a.steps)
+        e1.record(ctx.stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    prof = ctx.profile_read(reset=True)
+    ctx.profile(False)
+    launches = eng.launch_count() - launches0
+    chi_now = ctx.chi()
+    flags = ctx.flags()
+
+    # ---- end to end through the host-buffer C-ABI call: model upload + run + observable download per step
+    t_e2e = []
+    rec = None
+    for _ in range(max(2, min(a.steps, 3))):
+        barrier()
+        t0 = time.perf_counter()
+        rec = ctx.run_host(1, 1, False, gates=ens.gates, kick=kick)
+        torch.cuda.synchronize()
+        t_e2e.append(time.perf_counter() - t0)
+    h2d = ens.gates.nbytes + kick.nbytes
+    d2h = sum(v.nbytes for v in rec.values() if v is not None)
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- max over ranks, final gather of the observables (the only collective)
+    t = torch.tensor([ms, float(np.median(t_e2e)) * 1e3], dtype=torch.float64, device=f'cuda:{local}')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms = float(t[0]), float(t[1])
+    Z_all = gather_records(rec['Z'], world * R, axis=1, device=f'cuda:{local}')
+
+    if rank == 0:
+        ft, fs, fb = 0.0, 0.0, 0.0
+        for r in range(R):
+            x = update_flops(chi_now[r])
+            ft, fs, fb = ft + x[0], fs + x[1], fb + x[2]
+        fp64_peak = eng.probe_fp64(local, False) * 1e-3          # TFLOP/s, FMA pipe, measured now
+        dmma_peak = eng.probe_fp64(local, True) * 1e-3
+        svd_ms = prof['jacobi'][0] + prof['qr'][0] + prof['finalize'][0]
+        n_svd_launch = max(prof['jacobi'][1], 1)
+        jac_ms = prof['jacobi'][0] / n_svd_launch
+        # algorithmic SVD flops of one Jacobi launch = one parity layer of all chains; 4 layers per period
+        f_svd_launch = fs * a.steps / n_svd_launch
+        achieved = f_svd_launch / (svd_ms / n_svd_launch * 1e-3) * 1e-12 if svd_ms > 0 else None
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            peaks = {}
+        value = world * R * a.steps / (ms_max * 1e-3)
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+            'ms_per_step': ms_max / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'complex128 (f64)', 'data': 'synthetic',
+            'config': {'workload': workload_name(a), 'chains_total': world * R, 'L': L, 'chi_max': a.chi,
+                       'svds_per_step_per_chain': 2 * (L - 1), 'prep_periods': n_prep, 'prep_eps': a.prep_eps,
+                       'prep_s': round(t_prep, 2), 'chi_mid_min': int(chi_now[:, L // 2].min()),
+                       'chi_mean': float(chi_now[:, 1:-1].mean()),
+                       'l2': 'inputs (2.1 GB state + workspaces per step) larger than the 126 MB L2, no flush',
+                       'parallelism': f'independent chains sharded over {world} GPU(s), final gather only'},
+            'e2e': {'value': world * R / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
+                    'd2h_bytes_per_step': int(d2h),
+                    'note': 'tc_floquet_run_host: host gates+kick uploaded, observables (Z, entropies, overlap, chi) '
+                            'downloaded every step; the MPS state stays resident as it does in the reference'},
+            'gpu_launches': int(launches),
+            'clocks': clk,
+            'roofline': {
+                'bound': 'fp64', 'kernel': 'qr_kernel + jacobi_rows_kernel + finalize_kernel (batched truncated SVD)',
+                'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s',
+                'frac': (achieved / fp64_peak) if achieved else None,
+                'traffic': None,
+                'peak_source': 'tc_probe_fp64 (DFMA chain, all SMs) measured in this run; MEASURED_PEAKS.json has no '
+                               f'FP64 entry (hbm_gbs={peaks.get("hbm_gbs")}); DMMA probe {dmma_peak:.1f} TFLOP/s',
+                'flops_model': 'SURVEY 8d: 4(4m^2 n + 8 m n^2 + 9 n^3) per update, summed over the actual bond '
+                               'dimensions of every update in the launch',
+                'algorithmic_flops_per_launch': f_svd_launch,
+                'ms_per_launch': svd_ms / n_svd_launch,
+                'jacobi_ms_per_launch': jac_ms,
+                'step_share': {k: round(v[0] / ms, 4) for k, v in prof.items() if v[1]},
+                'whole_step_tflops': (ft + fs + fb) * a.steps / (ms * 1e-3) * 1e-12,
+            },
+            'svd_flags': flags,
+            'gathered_Z_shape': list(Z_all.shape),
+        }
+        # ---- CPU baseline on this box's host cores (bounded sample)
+        if not a.no_cpu:
+            try:
+                procs = min(os.cpu_count() or 1, 16)
+                r = cpu_ensemble_rate(a, 0, a.cpu_periods, procs=procs)
+                line['cpu_baseline'] = {
+                    'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
+                    'sample': f"{r['cores']} chains (one single-threaded process each) x {a.cpu_periods} periods of the "
+                              f"same workload at chi_max={r['chi_max']}, oracle/tebd_ref.py (NumPy + LAPACK zgesdd); "
+                              f"host has {os.cpu_count()} cores"}
+            except Exception as ex:   # the GPU number must not be lost to a host-side failure
+                line['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': 0, 'kind': 'port', 'sample': f'failed: {ex}'}
+        print(json.dumps(line), flush=True)
+    ens.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)

@@ -133,6 +133,19 @@ int tc_floquet_run_host(tc_ctx *ctx, const double *gates_host, const double *kic
                         double *ov_host, int32_t *chi_host);
 
 /* ---- diagnostics --------------------------------------------------------------------------- */
+/* per-kernel-class device timing with CUDA events on the context's stream (bench.py's roofline leg).
+   tc_profile_read synchronises, then writes the summed milliseconds and the number of timed launch
+   groups per class into ms_out[TC_PROF_NCLASS] / count_out[TC_PROF_NCLASS] (count_out may be NULL).   */
+#define TC_PROF_THETA 0    /* K1 theta GEMM (+ general-gate mix)      */
+#define TC_PROF_QR 1       /* K2a Householder QR preconditioner        */
+#define TC_PROF_JACOBI 2   /* K2b one-sided Jacobi sweeps              */
+#define TC_PROF_FINALIZE 3 /* K2c sort / truncate / renormalise / V^H  */
+#define TC_PROF_BLEFT 4    /* K3 B_i = C V_k GEMM                      */
+#define TC_PROF_MEASURE 5  /* observable kernels                       */
+#define TC_PROF_KICK 6     /* stand-alone kick                         */
+#define TC_PROF_NCLASS 8
+int tc_profile(tc_ctx *ctx, int enable);
+int tc_profile_read(tc_ctx *ctx, double *ms_out, long long *count_out, int reset);
 /* copy a workspace buffer of slot (r, bond position jb in the last layer) to the host             */
 int tc_dbg_get(tc_ctx *ctx, int which, int r, int jb, void *out_host, size_t bytes);
 /* count of kernel launches issued through this library since load                                */

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, 'libtc_b200.so')
 TRUNC_REFERENCE = 0
 TRUNC_TEBD = 1
 DBG_C, DBG_X, DBG_W, DBG_PERM = 0, 1, 2, 3
+PROF_CLASSES = ('theta_gemm', 'qr', 'jacobi', 'finalize', 'bleft_gemm', 'measure', 'kick', 'reserved')
 
 
 class EngineError(RuntimeError):
@@ -54,6 +55,8 @@ SIGNATURES = {
     'tc_correlation': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _D, _D, _D]),
     'tc_floquet_run_dev': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     'tc_floquet_run_host': (C.c_int, [_P, _D, _D, C.c_int, C.c_int, C.c_int, _D, _D, _D, _I]),
+    'tc_profile': (C.c_int, [_P, C.c_int]),
+    'tc_profile_read': (C.c_int, [_P, _D, C.POINTER(C.c_longlong), C.c_int]),
     'tc_dbg_get': (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_size_t]),
     'tc_launch_count': (C.c_longlong, []),
     'tc_probe_fp64': (C.c_int, [C.c_int, C.c_int, _D]),

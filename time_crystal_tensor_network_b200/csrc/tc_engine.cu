@@ -4,7 +4,8 @@
 // reference executes through MPS.apply_local_op, src/models/kicked_ising.py:162-188) the device runs
 //   K1  C = gate . (kick? B_i)(kick? B_{i+1})          DMMA GEMM, kick fused into the operand loads,
 //       theta = S_i C                                  diagonal Ising phase fused into the epilogue
-//   K2  J^H theta = Sigma V^H                          one-sided Jacobi on rows (tc_jacobi.cuh)
+//   K2  theta P = Q R (Q discarded), J^H R = Sigma V^H  Householder QR preconditioner, then one-sided
+//                                                      Jacobi on the rows of R (tc_jacobi.cuh)
 //       sort, truncate, renormalise, B_{i+1} = V_k^H   in-kernel
 //   K3  B_i = C V_k / |Sigma_k|                        DMMA GEMM (inverse-free update)
 // for every bond of a parity class and every chain in one launch each.
@@ -63,6 +64,41 @@ struct tc_ctx {
   // record buffers for tc_floquet_run_host
   void *rec = nullptr;
   size_t rec_bytes = 0;
+  // per-kernel-class CUDA-event timing (tc_profile): class, start, stop
+  bool profile = false;
+  struct Span {
+    int cls;
+    cudaEvent_t e0, e1;
+  };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> free_events;
+};
+
+static cudaEvent_t prof_event(tc_ctx *c) {
+  cudaEvent_t e;
+  if (!c->free_events.empty()) {
+    e = c->free_events.back();
+    c->free_events.pop_back();
+  } else {
+    cudaEventCreate(&e);
+  }
+  return e;
+}
+struct ProfScope {  // brackets the launches of one kernel class with events on the context's stream
+  tc_ctx *c;
+  tc_ctx::Span sp;
+  ProfScope(tc_ctx *ctx, int cls) : c(ctx) {
+    if (!c->profile) return;
+    sp.cls = cls;
+    sp.e0 = prof_event(c);
+    sp.e1 = prof_event(c);
+    cudaEventRecord(sp.e0, c->stream);
+  }
+  ~ProfScope() {
+    if (!c->profile) return;
+    cudaEventRecord(sp.e1, c->stream);
+    c->spans.push_back(sp);
+  }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -186,7 +222,7 @@ struct ThetaPolicy {
       const cplx ph = p0 ? (p1 ? g3 : g2) : (p1 ? g1 : g0);
       const cplx c = cmul(ph, v);
       C[o] = c;
-      X[o] = cscale(c, S[row >> 1]);
+      X[(size_t)row * N + 2 * (col - p1 * chiR) + p1] = cscale(c, S[row >> 1]);  // interleaved columns
     } else {
       C[o] = v;
     }
@@ -213,7 +249,7 @@ __global__ void __launch_bounds__(256) gate_mix_kernel(TcDev d, LayerArgs a) {
     cplx acc = cmake(0.0, 0.0);
     for (int q = 0; q < 4; ++q) cfma(acc, g[p * 4 + q], t[q]);
     C[o[p]] = acc;
-    X[o[p]] = cscale(acc, s);
+    X[(size_t)(2 * al + (p >> 1)) * b.N + 2 * be + (p & 1)] = cscale(acc, s);  // interleaved columns
   }
 }
 
@@ -304,19 +340,36 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
   for (int r0 = r_lo; r0 < r_hi; r0 += d.ws_chains) {
     const int nr = (r_hi - r0) < d.ws_chains ? (r_hi - r0) : d.ws_chains;
     LayerArgs a{first_site, 2, nb, r0, nr, kick_mode, gate_override, diag};
-    tcg::gemm_kernel<ThetaPolicy><<<dim3(tiles, nb, nr), tcg::NT, 0, c->stream>>>(d, a);
-    LAUNCHED();
-    if (!diag) {
-      const int gx = (d.chi_cap * d.chi_cap + 255) / 256;
-      gate_mix_kernel<<<dim3(gx, nb, nr), 256, 0, c->stream>>>(d, a);
+    {
+      ProfScope ps(c, TC_PROF_THETA);
+      tcg::gemm_kernel<ThetaPolicy><<<dim3(tiles, nb, nr), tcg::NT, 0, c->stream>>>(d, a);
+      LAUNCHED();
+      if (!diag) {
+        const int gx = (d.chi_cap * d.chi_cap + 255) / 256;
+        gate_mix_kernel<<<dim3(gx, nb, nr), 256, 0, c->stream>>>(d, a);
+        LAUNCHED();
+      }
+    }
+    {
+      ProfScope ps(c, TC_PROF_QR);
+      tcj::qr_kernel<<<dim3(nb, nr), tcj::NT, (d.n2 + 64) * sizeof(cplx), c->stream>>>(d, a);
       LAUNCHED();
     }
-    tcj::jacobi_rows_kernel<<<dim3(nb, nr), tcj::NT, d.n2 * sizeof(double), c->stream>>>(d, a);
-    LAUNCHED();
-    tcj::finalize_kernel<<<dim3(nb, nr), tcj::NT, d.n2 * sizeof(double), c->stream>>>(d, a);
-    LAUNCHED();
-    tcg::gemm_kernel<BLPolicy><<<dim3(tiles, nb, nr), tcg::NT, 0, c->stream>>>(d, a);
-    LAUNCHED();
+    {
+      ProfScope ps(c, TC_PROF_JACOBI);
+      tcj::jacobi_rows_kernel<<<dim3(nb, nr), tcj::NT, d.n2 * sizeof(double), c->stream>>>(d, a);
+      LAUNCHED();
+    }
+    {
+      ProfScope ps(c, TC_PROF_FINALIZE);
+      tcj::finalize_kernel<<<dim3(nb, nr), tcj::NT, d.n2 * sizeof(double), c->stream>>>(d, a);
+      LAUNCHED();
+    }
+    {
+      ProfScope ps(c, TC_PROF_BLEFT);
+      tcg::gemm_kernel<BLPolicy><<<dim3(tiles, nb, nr), tcg::NT, 0, c->stream>>>(d, a);
+      LAUNCHED();
+    }
   }
   return 0;
 }
@@ -329,6 +382,7 @@ static int run_layer(tc_ctx *c, int parity, int kick_mode) {
 }
 
 static int run_kick_all(tc_ctx *c) {
+  ProfScope ps(c, TC_PROF_KICK);
   tco::one_site_kernel<<<dim3(c->d.L, c->d.R), 256, 0, c->stream>>>(c->d, 0, 0, nullptr);
   LAUNCHED();
   return 0;
@@ -347,6 +401,7 @@ static int run_period(tc_ctx *c) {
 
 static int measure_into(tc_ctx *c, double *rdm, double *Z, double *ent, double *ov, int32_t *chi) {
   const TcDev &d = c->d;
+  ProfScope ps(c, TC_PROF_MEASURE);
   if (rdm || Z || ent) {
     tco::measure_kernel<<<dim3(d.L, d.R), tco::NT, 0, c->stream>>>(d, rdm, Z, ent);
     LAUNCHED();
@@ -474,6 +529,11 @@ int tc_ctx_destroy(tc_ctx *c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  for (auto &sp : c->spans) {
+    cudaEventDestroy(sp.e0);
+    cudaEventDestroy(sp.e1);
+  }
+  for (auto e : c->free_events) cudaEventDestroy(e);
   if (c->rec) cudaFree(c->rec);
   if (c->own_arena) cudaFree(c->arena);
   if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -500,6 +560,35 @@ int tc_get_flags(tc_ctx *c, int32_t *out4) {
   CTX(c);
   CK(cudaMemcpyAsync(out4, c->d.flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int tc_profile(tc_ctx *c, int enable) {
+  if (!c) return fail("null context");
+  c->profile = enable != 0;
+  return 0;
+}
+
+int tc_profile_read(tc_ctx *c, double *ms_out, long long *count_out, int reset) {
+  CTX(c);
+  CK(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < TC_PROF_NCLASS; ++k) {
+    ms_out[k] = 0.0;
+    if (count_out) count_out[k] = 0;
+  }
+  for (auto &sp : c->spans) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, sp.e0, sp.e1));
+    ms_out[sp.cls] += ms;
+    if (count_out) count_out[sp.cls] += 1;
+  }
+  if (reset) {
+    for (auto &sp : c->spans) {
+      c->free_events.push_back(sp.e0);
+      c->free_events.push_back(sp.e1);
+    }
+    c->spans.clear();
+  }
   return 0;
 }
 

@@ -193,6 +193,17 @@ class Context:
         check(self.lib.tc_floquet_run_dev(self._h, n_steps, measure_every, rec0, int(measure_now),
                                           p(Z), p(ent), p(ov), p(chi)), 'tc_floquet_run_dev')
 
+    def profile(self, enable=True):
+        check(self.lib.tc_profile(self._h, int(enable)), 'tc_profile')
+
+    def profile_read(self, reset=True):
+        """{kernel class: (milliseconds, timed launch groups)} since the last reset (synchronises)."""
+        ms = np.zeros(8, dtype=np.float64)
+        cnt = np.zeros(8, dtype=np.int64)
+        check(self.lib.tc_profile_read(self._h, dptr(ms), cnt.ctypes.data_as(C.POINTER(C.c_longlong)), int(reset)),
+              'tc_profile_read')
+        return {name: (float(ms[k]), int(cnt[k])) for k, name in enumerate(_lib.PROF_CLASSES)}
+
     def dbg_get(self, which, r, jb, shape, dtype):
         out = np.empty(shape, dtype=dtype)
         check(self.lib.tc_dbg_get(self._h, which, r, jb, out.ctypes.data_as(C.c_void_p), out.nbytes), 'tc_dbg_get')
