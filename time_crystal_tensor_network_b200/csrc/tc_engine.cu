@@ -23,6 +23,7 @@
 #include "tc_common.cuh"
 #include "tc_gemm.cuh"
 #include "tc_jacobi.cuh"
+#include "tc_jacobi_blocked.cuh"
 #include "tc_observe.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -61,6 +62,8 @@ struct tc_ctx {
   cplx *E0 = nullptr, *E1 = nullptr, *Tt = nullptr;  // transfer contraction scratch
   double *small_out = nullptr;                       // 8 doubles
   bool have_model = false;
+  bool blocked_attr_set = false;
+  bool force_simple_jacobi = false;  // TC_JACOBI=simple: the warp-per-pair kernel for every size (A/B testing)
   // record buffers for tc_floquet_run_host
   void *rec = nullptr;
   size_t rec_bytes = 0;
@@ -357,7 +360,16 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
     }
     {
       ProfScope ps(c, TC_PROF_JACOBI);
-      tcj::jacobi_rows_kernel<<<dim3(nb, nr), tcj::NT, d.n2 * sizeof(double), c->stream>>>(d, a);
+      if (d.n2 <= tcb::MAX_N && !c->force_simple_jacobi) {
+        const size_t smem = (size_t)3 * tcb::BR * d.n2 * sizeof(cplx) + d.n2 * sizeof(double) + 64;
+        if (!c->blocked_attr_set) {
+          CK(cudaFuncSetAttribute(tcb::jacobi_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          c->blocked_attr_set = true;
+        }
+        tcb::jacobi_blocked_kernel<<<dim3(nb, nr), tcb::NT, smem, c->stream>>>(d, a);
+      } else {
+        tcj::jacobi_rows_kernel<<<dim3(nb, nr), tcj::NT, d.n2 * sizeof(double), c->stream>>>(d, a);
+      }
       LAUNCHED();
     }
     {
@@ -462,6 +474,7 @@ int tc_ctx_create(int device, int L, int chi_cap, int R, void *arena, size_t are
     c->own_arena = true;
   }
   c->arena_bytes = lo.total;
+  if (const char *e = getenv("TC_JACOBI")) c->force_simple_jacobi = strcmp(e, "simple") == 0;
   if (stream) {
     c->stream = (cudaStream_t)stream;
   } else {
