@@ -216,7 +216,7 @@ def run_ours(a):
         torch.cuda.synchronize()
 
     # ---- device-resident timing: W warm-up steps, then exactly K steps
-    # L2 note: one step streams the whole 2.1 GB (R=32) state plus 2 x 1 MiB workspaces per update
+    # L2 note: one step streams the 0.54 GB (R=32) state plus 2 x 1 MiB workspaces per update
     # through the 126 MB L2, i.e. inputs are far larger than L2; no explicit flush is needed.
     for _ in range(a.warmup):
         ctx.floquet_step(1)
@@ -287,7 +287,7 @@ def run_ours(a):
                        'svds_per_step_per_chain': 2 * (L - 1), 'prep_periods': n_prep, 'prep_eps': a.prep_eps,
                        'prep_s': round(t_prep, 2), 'chi_mid_min': int(chi_now[:, L // 2].min()),
                        'chi_mean': float(chi_now[:, 1:-1].mean()),
-                       'l2': 'inputs (2.1 GB state + workspaces per step) larger than the 126 MB L2, no flush',
+                       'l2': 'working set (0.54 GB state + 1.07 GB per-layer workspaces at 32 chains) far larger than the 126 MB L2, no flush',
                        'parallelism': f'independent chains sharded over {world} GPU(s), final gather only'},
             'e2e': {'value': world * R / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
                     'd2h_bytes_per_step': int(d2h),

@@ -1,0 +1,157 @@
+"""CPU suite, part 2: host-side logic of the product (no GPU): spectral post-processing against the
+golden vectors, the C-ABI library's symbol table against include/tc_b200.h, loud failure without CUDA,
+sharding helpers (incl. a world_size-2 gloo run), bench bookkeeping."""
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_spectral_postprocessing_matches_reference(golden):
+    from time_crystal_tensor_network_b200.core import observables as obs
+    for key, ent in golden['post'].items():
+        name, T = key.split('|T=')
+        period = float(T)
+        s = np.array(golden['series'][name])
+        t = np.arange(len(s)) * period
+        fund, sub = obs.subharmonic_response(list(s), period)
+        assert [float(fund), float(sub)] == ent['subharmonic_response']
+        assert obs.extract_subharmonic_amplitude(t, s, period) == ent['extract_subharmonic_amplitude']
+        assert obs.extract_subharmonic_amplitude_from_loschmidt(t, s, period) == ent['extract_from_loschmidt']
+        assert float(obs.detect_period_doubling_from_loschmidt(list(np.abs(s)))) == ent['detect_period_doubling']
+    assert float(obs.fidelity_decay(list(np.exp(-0.05 * np.arange(20) * 2.0)), list(np.arange(20) * 2.0))) == \
+        golden['fidelity_decay']
+    # 31-sample +-1 series, period 2 -> positive-frequency bin 14 of 15, amplitude 1.0
+    k = np.arange(31)
+    assert obs.extract_subharmonic_amplitude(k * 2.0, (-1.0) ** k, 2.0) == 1.0
+    assert obs.extract_subharmonic_amplitude(np.arange(5.0), np.ones(5), 2.0) == 0.0
+
+
+def test_pauli_and_unused_gate_helper(golden):
+    from time_crystal_tensor_network_b200.core.tensor_utils import pauli_matrices, create_time_evolution_gates
+    p = pauli_matrices()
+    for k, v in golden['pauli'].items():
+        assert np.array_equal(p[k], np.array(v['re']) + 1j * np.array(v['im']))
+    assert np.allclose(p['X'] @ p['Y'], 1j * p['Z'])
+    g = create_time_evolution_gates(1.0, 0.3, 0.5, 4)
+    # literal reproduction of the reference's element-wise exp: off-diagonal entries are exp(0) = 1
+    assert g['ising_evolution'][0, 1] == 1.0 and g['pi_pulse'][0, 0] == 1.0
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'tc_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(tc_[A-Za-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from time_crystal_tensor_network_b200 import _lib
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f'{n} declared in include/tc_b200.h but not exported'
+        assert n in _lib.SIGNATURES, f'{n} has no ctypes prototype'
+    assert set(_lib.SIGNATURES) == set(names)
+    assert lib.tc_version() >= 100
+    assert lib.tc_ctx_arena_bytes(32, 128, 32) > 1.5 * 1024 ** 3     # 0.5 GiB of state + 1 GiB of workspaces
+    assert lib.tc_ctx_arena_bytes(0, 1, 1) == 0
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is visible')
+    from time_crystal_tensor_network_b200.engine import Context, EngineError
+    from time_crystal_tensor_network_b200.core.tensor_utils import create_initial_state
+    with pytest.raises(EngineError):
+        Context(4, 2, 1)
+    with pytest.raises(EngineError):
+        create_initial_state(4, 'neel')
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'time_crystal_tensor_network_b200')
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh')):
+                assert 'oracle' not in open(os.path.join(base, f)).read(), f'{f} mentions the oracle'
+
+
+def test_shard_bounds():
+    from time_crystal_tensor_network_b200.sharding import shard_bounds, shard_sizes
+    for n in (0, 1, 7, 32, 256, 1024, 1025):
+        for w in (1, 2, 3, 4, 8):
+            spans = [shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[r][1] == spans[r + 1][0] for r in range(w - 1))
+            sizes = shard_sizes(n, w)
+            assert max(sizes) - min(sizes) <= 1 and sum(sizes) == n
+    assert shard_bounds(256, 8, 3) == (96, 128)
+    with pytest.raises(ValueError):
+        shard_bounds(4, 2, 2)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from time_crystal_tensor_network_b200.sharding import shard_bounds, gather_records, disorder_average
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
+    n, T, L = 5, 3, 4                                    # ragged: shards of 3 and 2 chains
+    full = np.arange(T * n * L, dtype=float).reshape(T, n, L)
+    lo, hi = shard_bounds(n, world, rank)
+    got = gather_records(full[:, lo:hi], n, axis=1)
+    cfull = full + 1j * full[::-1]
+    cgot = gather_records(cfull[:, lo:hi], n, axis=1)
+    avg = disorder_average(full[:, lo:hi].sum(axis=1), hi - lo)
+    q.put((rank, np.array_equal(got, full), np.array_equal(cgot, cfull), np.allclose(avg, full.mean(axis=1))))
+    dist.destroy_process_group()
+
+
+def test_gather_world_size_two_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r[0] for r in res) == [0, 1]
+    assert all(r[1] and r[2] and r[3] for r in res)
+
+
+def test_bench_flop_model():
+    sys.path.insert(0, ROOT)
+    import bench
+    L, chi = 32, 128
+    ft, fs, fb = bench.update_flops(np.full(L + 1, chi))
+    # uniform-chi count of SURVEY 8d: (32 + 672 + 32) chi^3 per update, 2(L-1) updates per period
+    n = 2 * (L - 1)
+    assert ft == n * 32 * chi ** 3 and fb == n * 32 * chi ** 3 and fs == n * 672 * chi ** 3
+
+
+def test_reference_import_layout():
+    """With only <repo>/src on sys.path the reference's import lines work unchanged (main.py:32-37)."""
+    import subprocess
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from core.tensor_utils import create_initial_state, pauli_matrices\n"
+        "from core.observables import calculate_loschmidt_echo, staggered_magnetization, magnetization\n"
+        "from core import create_initial_state as c2\n"
+        "from models.kicked_ising import KickedIsingModel\n"
+        "from models import KickedIsingModel as K2\n"
+        "from dynamics.tebd_evolution import TEBDEvolution, CustomFloquet\n"
+        "from dynamics import TEBDEvolution as T2\n"
+        "m = KickedIsingModel(4, 1.0, 0.2, 1.0, disorder_seed=42)\n"
+        "print(repr(float(m.h_fields[0])), len(m.ising_gates), m.pi_pulse_gate[0, 1])\n"
+    ) % os.path.join(ROOT, 'src')
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd='/')
+    assert out.returncode == 0, out.stderr
+    assert abs(float(out.stdout.split()[0]) + 0.050183952461055) < 1e-16 and out.stdout.split()[1] == '3'
