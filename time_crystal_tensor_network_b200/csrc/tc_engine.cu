@@ -355,7 +355,10 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
     }
     {
       ProfScope ps(c, TC_PROF_QR);
-      tcj::qr_kernel<<<dim3(nb, nr), tcj::NT, (d.n2 + 64) * sizeof(cplx), c->stream>>>(d, a);
+      if (d.n2 <= tcj::QMAXM && !c->force_simple_jacobi)
+        tcj::qr_blocked_kernel<<<dim3(nb, nr), tcj::QNT, 0, c->stream>>>(d, a);
+      else
+        tcj::qr_kernel<<<dim3(nb, nr), tcj::NT, (d.n2 + 64) * sizeof(cplx), c->stream>>>(d, a);
       LAUNCHED();
     }
     {

@@ -134,6 +134,174 @@ __global__ void __launch_bounds__(NT) qr_kernel(TcDev d, LayerArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// K2a fast path (M <= 256 rows): blocked Householder QR, panels of QB columns.
+//   panel:    one row per thread, the panel row in registers; per column one batched block reduction
+//             (|x|^2 and the v^H a products for the remaining panel columns); reflectors V to smem
+//   T:        compact WY factor, H_0 ... H_{QB-1} = I - V T V^H (larft forward/columnwise)
+//   trailing: thread per column, W = V^H A (one pass), W <- T^H W, A -= V W (second pass):
+//             two passes over the trailing matrix per PANEL instead of per column.
+// static smem: V 32 KB + reduction scratch
+// ------------------------------------------------------------------------------------------------
+constexpr int QB = 8, QNT = 256, QMAXM = 256;
+
+// block-wide sums of NV doubles per thread; result in out[0..NV) (all threads), scratch [QNT/32][NV]
+template <int NV>
+__device__ __forceinline__ void block_sum_vec(double (&v)[NV], double *scratch, int nv_used) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+    if (k < nv_used)
+      for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  __syncthreads();
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+      if (k < nv_used) scratch[warp * NV + k] = v[k];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+    if (k < nv_used) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < QNT / 32; ++w) t += scratch[w * NV + k];
+      v[k] = t;
+    }
+}
+
+__global__ void __launch_bounds__(QNT) qr_blocked_kernel(TcDev d, LayerArgs a) {
+  Bond b;
+  if (!get_bond(d, a, blockIdx.x, blockIdx.y, b)) return;
+  const int M = b.M, N = b.N;
+  cplx *X = d.Xw + b.slot * d.slot_stride;
+  __shared__ __align__(16) cplx V[QMAXM * QB];
+  __shared__ __align__(16) cplx Tm[QB * QB];
+  __shared__ double scratch[(QNT / 32) * 2 * QB];
+  __shared__ cplx s_alpha;
+  const int tid = threadIdx.x;
+  const int steps = (M - 1) < N ? (M - 1) : N;  // columns that have something to annihilate
+  for (int k0 = 0; k0 < steps; k0 += QB) {
+    const int nbw = (steps - k0) < QB ? (steps - k0) : QB;  // reflectors in this panel
+    const int pw = (N - k0) < QB ? (N - k0) : QB;           // panel columns present
+    const int rows = M - k0;                                // panel rows, one per thread
+    const bool have = tid < rows;
+    cplx p[QB];
+#pragma unroll
+    for (int j = 0; j < QB; ++j) p[j] = (have && j < pw) ? X[(size_t)(k0 + tid) * N + k0 + j] : cmake(0.0, 0.0);
+    cplx tau[QB];
+#pragma unroll
+    for (int j = 0; j < QB; ++j) {
+      tau[j] = cmake(0.0, 0.0);
+      if (j < nbw) {
+        // |x|^2 below the diagonal of column j
+        double red[2 * QB];
+        red[0] = (have && tid > j) ? cabs2(p[j]) : 0.0;
+        if (tid == j) s_alpha = p[j];
+        block_sum_vec<2 * QB>(red, scratch, 1);
+        double beta;
+        cplx sc;
+        larfg(s_alpha, red[0], beta, tau[j], sc);
+        const cplx v = (tid == j) ? cmake(1.0, 0.0) : ((have && tid > j) ? cmul(p[j], sc) : cmake(0.0, 0.0));
+        V[tid * QB + j] = v;
+        if (tau[j].x != 0.0 || tau[j].y != 0.0) {
+          // w_c = conj(tau) sum_r conj(v_r) p_r[c] for the remaining panel columns
+#pragma unroll
+          for (int c = 0; c < QB; ++c) {
+            cplx t = cmake(0.0, 0.0);
+            if (c > j) cfmac(t, v, p[c]);
+            red[2 * c] = t.x;
+            red[2 * c + 1] = t.y;
+          }
+          block_sum_vec<2 * QB>(red, scratch, 2 * QB);
+          const cplx tc = cconj(tau[j]);
+#pragma unroll
+          for (int c = 0; c < QB; ++c)
+            if (c > j) {
+              const cplx w = cmul(tc, cmake(red[2 * c], red[2 * c + 1]));
+              const cplx m = cmul(v, w);
+              p[c] = csub(p[c], m);
+            }
+          if (tid == j) p[j] = cmake(beta, 0.0);
+          if (tid > j) p[j] = cmake(0.0, 0.0);
+        } else {
+          __syncthreads();  // keep the barrier count uniform with the branch above
+          __syncthreads();
+        }
+      } else {
+        V[tid * QB + j] = cmake(0.0, 0.0);
+      }
+    }
+    // R part of the panel back to global
+    if (have)
+#pragma unroll
+      for (int j = 0; j < QB; ++j)
+        if (j < pw) X[(size_t)(k0 + tid) * N + k0 + j] = p[j];
+    __syncthreads();
+    // ---- T: T[j][j] = tau_j, T[0:j, j] = -tau_j T[0:j,0:j] (V[:,0:j]^H v_j)
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      __shared__ cplx G[QB * QB];
+      for (int pr = warp; pr < QB * QB; pr += QNT / 32) {
+        const int i = pr / QB, j = pr % QB;
+        if (i < j) {
+          cplx acc = cmake(0.0, 0.0);
+          for (int r = lane; r < rows; r += 32) cfmac(acc, V[r * QB + i], V[r * QB + j]);
+          acc.x = warp_sum(acc.x);
+          acc.y = warp_sum(acc.y);
+          if (lane == 0) G[pr] = acc;
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        for (int j = 0; j < QB; ++j) {
+          for (int i = 0; i < QB; ++i) Tm[i * QB + j] = cmake(0.0, 0.0);
+          Tm[j * QB + j] = tau[j];
+          for (int i = 0; i < j; ++i) {
+            cplx acc = cmake(0.0, 0.0);
+            for (int l = i; l < j; ++l) cfma(acc, Tm[i * QB + l], G[l * QB + j]);
+            const cplx mt = cmake(-tau[j].x, -tau[j].y);
+            Tm[i * QB + j] = cmul(mt, acc);
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // ---- trailing columns: A <- (I - V T^H V^H) A
+    const int c = k0 + QB + tid;
+    if (c < N) {
+      cplx *col = X + (size_t)k0 * N + c;
+      cplx W[QB];
+#pragma unroll
+      for (int j = 0; j < QB; ++j) W[j] = cmake(0.0, 0.0);
+      for (int r = 0; r < rows; ++r) {
+        const cplx av = col[(size_t)r * N];
+        const cplx *vr = V + r * QB;
+#pragma unroll
+        for (int j = 0; j < QB; ++j) cfmac(W[j], vr[j], av);
+      }
+      cplx W2[QB];
+#pragma unroll
+      for (int i = 0; i < QB; ++i) {
+        cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+        for (int j = 0; j < QB; ++j)
+          if (j <= i) cfmac(acc, Tm[j * QB + i], W[j]);
+        W2[i] = acc;
+      }
+      for (int r = 0; r < rows; ++r) {
+        cplx av = col[(size_t)r * N];
+        const cplx *vr = V + r * QB;
+        cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+        for (int j = 0; j < QB; ++j) cfma(acc, vr[j], W2[j]);
+        col[(size_t)r * N] = csub(av, acc);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // v1: warp per row pair, rows streamed from L1/L2.  dynamic smem: n2 doubles (row norms^2)
 // ------------------------------------------------------------------------------------------------
