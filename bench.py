@@ -114,11 +114,7 @@ class Clocks:
 def _cpu_worker(task):
     """Prepare one chain on the CPU (oracle O2, TEBD truncation) and time `n_timed` periods."""
     seed, L, chi, eps, prep_eps, prep_max, n_warm, n_timed, threads = task
-    try:
-        from threadpoolctl import threadpool_limits
-        limiter = threadpool_limits(limits=threads)
-    except Exception:
-        limiter = None
+    sys.path.insert(0, ROOT)
     from oracle import tebd_ref
     h = tebd_ref.disorder_fields(L, WORK['W'], seed)
     trunc = dict(chi_max=chi, svd_min=WORK['svd_min'], trunc_cut=WORK['trunc_cut'])
@@ -135,7 +131,6 @@ def _cpu_worker(task):
     for _ in range(n_timed):
         psi, _ = tebd_ref.floquet_step(psi, kick, gates, mode='tebd', trunc=trunc)
     dt = time.perf_counter() - t0
-    del limiter
     return dt, n_prep, max(psi.chi)
 
 
@@ -145,9 +140,20 @@ def cpu_ensemble_rate(a, n_warm, n_timed, procs=None):
     cores = os.cpu_count() or 1
     procs = procs or cores
     tasks = [(WORK['seed0'] + r, a.L, a.chi, a.eps, a.prep_eps, a.prep_max, n_warm, n_timed, 1) for r in range(procs)]
+    # spawn (not fork) with single-threaded BLAS set through the environment: a forked child inherits an
+    # OpenBLAS pool sized for all cores and 8 such children oversubscribe the box 8x
+    keep = {k: os.environ.get(k) for k in ('OPENBLAS_NUM_THREADS', 'OMP_NUM_THREADS', 'MKL_NUM_THREADS')}
+    os.environ.update({k: '1' for k in keep})
     t0 = time.perf_counter()
-    with mp.get_context('fork').Pool(procs) as pool:
-        res = pool.map(_cpu_worker, tasks)
+    try:
+        with mp.get_context('spawn').Pool(procs) as pool:
+            res = pool.map(_cpu_worker, tasks)
+    finally:
+        for k, v in keep.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     wall = time.perf_counter() - t0
     slowest = max(r[0] for r in res)
     return {'value': procs * n_timed / slowest, 'cores': procs, 'ms_per_step': slowest / n_timed * 1e3,
@@ -243,7 +249,7 @@ def run_ours(a):
 
     # ---- end to end through the host-buffer C-ABI call: model upload + run + observable download per step
     t_e2e = []
-    rec = None
+    rec = ctx.run_host(1, 1, False, gates=ens.gates, kick=kick)      # untimed: allocates the record buffers
     for _ in range(max(2, min(a.steps, 3))):
         barrier()
         t0 = time.perf_counter()

@@ -56,7 +56,8 @@ int tc_ctx_destroy(tc_ctx *ctx);
 int tc_sync(tc_ctx *ctx);
 int tc_ctx_info(tc_ctx *ctx, int *L, int *chi_cap, int *R, int *device);
 /* health counters since context creation: out[0] = updates truncated by chi_cap (overflow), out[1] = SVDs
-   that hit the sweep limit, out[2] = largest number of Jacobi sweeps any SVD needed, out[3] = 0        */
+   that hit the sweep limit, out[2] = largest number of Jacobi sweeps any SVD needed, out[3] = 100 x mean sweeps of the SVDs with
+   at least 128 rows (fast path only)                                                              */
 int tc_get_flags(tc_ctx *ctx, int32_t *out4);
 
 /* ---- state --------------------------------------------------------------------------------- */

@@ -27,6 +27,7 @@ from . import tebd_ref
 EPS = np.finfo(float).eps
 DEAD_REL2 = 1e-30          # rows with |x|^2 < DEAD_REL2 |theta|_F^2 are numerically zero (tc_jacobi.cuh)
 MAX_SWEEPS = 48
+SMALL_REL2 = 1e-16       # a sweep whose rotations were all below 1e-8 relative ends the iteration
 
 
 def interleave_perm(chi_r):
@@ -90,7 +91,7 @@ def jacobi_rows(X, tol=None, max_sweeps=MAX_SWEEPS):
     hist = []
     for _sweep in range(max_sweeps):
         nrm2 = np.sum(np.abs(X) ** 2, axis=1)
-        nrot = 0
+        nrot = nbig = 0
         for r in range(M - 1):
             I, J = rr_pairs(M, r)
             ai, aj = nrm2[I], nrm2[J]
@@ -100,6 +101,7 @@ def jacobi_rows(X, tol=None, max_sweeps=MAX_SWEEPS):
                 continue
             I, J, g, ai, aj = I[act], J[act], g[act], ai[act], aj[act]
             ga = np.abs(g)
+            nbig += int(np.sum(ga * ga > SMALL_REL2 * ai * aj))
             dd = aj - ai
             t = np.copysign(2 * ga / (np.abs(dd) + np.sqrt(dd * dd + 4 * ga * ga)), dd)
             cs = 1 / np.sqrt(1 + t * t)
@@ -110,7 +112,7 @@ def jacobi_rows(X, tol=None, max_sweeps=MAX_SWEEPS):
             nrm2[I], nrm2[J] = ai - t * ga, aj + t * ga
             nrot += int(act.sum())
         hist.append(nrot)
-        if nrot == 0:
+        if nbig == 0:       # only rotations below 1e-8 relative (or none): converged (tc_jacobi.cuh)
             break
     return X, hist
 

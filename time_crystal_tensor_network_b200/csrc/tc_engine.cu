@@ -364,7 +364,7 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
     {
       ProfScope ps(c, TC_PROF_JACOBI);
       if (d.n2 <= tcb::MAX_N && !c->force_simple_jacobi) {
-        const size_t smem = (size_t)3 * tcb::BR * d.n2 * sizeof(cplx) + d.n2 * sizeof(double) + 64;
+        const size_t smem = (size_t)3 * tcb::BR * d.n2 * sizeof(cplx) + d.n2 * sizeof(double) + 64 + 2 * tcb::BR * sizeof(int);
         if (!c->blocked_attr_set) {
           CK(cudaFuncSetAttribute(tcb::jacobi_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           c->blocked_attr_set = true;
@@ -508,6 +508,8 @@ int tc_ctx_create(int device, int L, int chi_cap, int R, void *arena, size_t are
   d.gates = c->gates_dev;
   d.kick = c->kick_dev;
   d.gates_diag = 0;
+  d.rot64 = 1;  // bit0: FP64 rotation angle (measured faster than the FP32/SFU variant on B200); bit1: lockstep rounds
+  if (const char *e = getenv("TC_ROT64")) d.rot64 = atoi(e);
   d.trunc_err = (double *)(base + lo.trunc_err);
   d.flags = (int *)(base + lo.flags);
   d.Cw = (cplx *)(base + lo.Cw);
@@ -574,11 +576,15 @@ int tc_ctx_info(tc_ctx *c, int *L, int *chi_cap, int *R, int *device) {
 
 int tc_get_flags(tc_ctx *c, int32_t *out4) {
   CTX(c);
-  CK(cudaMemcpyAsync(out4, c->d.flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  int tmp[8];
+  CK(cudaMemcpyAsync(tmp, c->d.flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  out4[0] = tmp[0];
+  out4[1] = tmp[1];
+  out4[2] = tmp[2];
+  out4[3] = tmp[4] > 0 ? (int)(100.0 * tmp[3] / tmp[4]) : 0;  // mean sweeps x 100 over the SVDs with >= 128 rows
   return 0;
 }
-
 int tc_profile(tc_ctx *c, int enable) {
   if (!c) return fail("null context");
   c->profile = enable != 0;

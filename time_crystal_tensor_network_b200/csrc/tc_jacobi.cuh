@@ -21,6 +21,10 @@
 namespace tcj {
 constexpr int NT = 256;
 constexpr int MAX_SWEEPS = 48;
+// A sweep whose rotations all had relative off-diagonal |g|/sqrt(a_i a_j) below 1e-8 ends the
+// iteration: by quadratic convergence what is left is below 1e-16 (checked on TEBD matrices: the final
+// orthogonality is identical to running the extra verification sweep).
+constexpr double SMALL_REL2 = 1e-16;
 constexpr double DEAD_REL2 = 1e-30;  // rows with |x|^2 < DEAD_REL2 * |theta|_F^2 are numerically zero
 
 // round-robin tournament (circle method): pair k of round r among M players (M even)
@@ -357,6 +361,7 @@ __global__ void __launch_bounds__(NT) jacobi_rows_kernel(TcDev d, LayerArgs a) {
         gi = warp_sum(gi);
         const double g2 = gr * gr + gi * gi;
         if (!(g2 > tol2 * ai * aj)) continue;
+        nrot += g2 > SMALL_REL2 * ai * aj;
         const double ga = sqrt(g2);
         const double zeta = (aj - ai) / (2.0 * ga);
         const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
@@ -379,7 +384,6 @@ __global__ void __launch_bounds__(NT) jacobi_rows_kernel(TcDev d, LayerArgs a) {
           nrm2[i] = ai - t * ga;
           nrm2[j] = aj + t * ga;
         }
-        ++nrot;
       }
       __syncthreads();
     }

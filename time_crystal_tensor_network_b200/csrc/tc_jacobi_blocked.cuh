@@ -53,22 +53,53 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct Rot {
-  double cs, sr, si, tg;  // cos, s*e (complex), t*|g|
+  double cs, sr, si, ni, nj;  // cos, s*e (complex), new squared norms
 };
 
-// rotation that orthogonalises two rows with squared norms ai, aj and g = x_i . conj(x_j)
-__device__ __forceinline__ bool make_rot(double ai, double aj, double gr, double gi, double tol2, Rot &r) {
+// Rotation that orthogonalises two rows with squared norms ai, aj and g = x_i . conj(x_j).
+// The rotation ANGLE is computed in FP32 (SFU rsqrt/rcp instead of ~60 dependent FP64 instructions):
+// any tau gives an exactly unitary transformation c [[1, -tau], [conj(tau), 1]] as long as
+// c = 1/sqrt(1 + |tau|^2) is formed in FP64 from the tau that is actually applied; an FP32-accurate
+// angle only leaves a residual ~1e-7 |g|, which the quadratically convergent sweeps absorb.
+// The norm updates use the exact identities for the applied tau.
+__device__ __forceinline__ bool make_rot(double ai, double aj, double gr, double gi, double tol2, Rot &r,
+                                         int rot64) {
   const double g2 = gr * gr + gi * gi;
   if (!(g2 > tol2 * ai * aj)) return false;
-  const double rg = rsqrt(g2), ga = g2 * rg;
-  const double dd = aj - ai;
-  const double h = sqrt(fma(dd, dd, 4.0 * g2));
-  const double t = copysign(2.0 * ga / (fabs(dd) + h), dd);
-  r.cs = rsqrt(fma(t, t, 1.0));
-  const double sn = r.cs * t;
-  r.sr = sn * gr * rg;
-  r.si = sn * gi * rg;
-  r.tg = t * ga;
+  if (rot64) {  // all-FP64 angle (A/B switch TC_ROT64=1)
+    const double rg = rsqrt(g2), ga = g2 * rg;
+    const double dd = aj - ai;
+    const double h = sqrt(fma(dd, dd, 4.0 * g2));
+    const double t = copysign(2.0 * ga / (fabs(dd) + h), dd);
+    r.cs = rsqrt(fma(t, t, 1.0));
+    const double sn = r.cs * t;
+    r.sr = sn * gr * rg;
+    r.si = sn * gi * rg;
+    r.ni = ai - t * ga;
+    r.nj = aj + t * ga;
+    return true;
+  }
+  // scale by an exact power of two so that max(ai, aj) is O(1) in float
+  const double m = fmax(ai, aj);
+  const int hi = __double2hiint(m);
+  const double sc = __hiloint2double((2046 << 20) - (hi & 0x7ff00000), 0);  // 2^-exponent(m)
+  const float fd = (float)((aj - ai) * sc);
+  const float fr = (float)(gr * sc), fi = (float)(gi * sc);
+  const float mx = fmaxf(fabsf(fr), fabsf(fi)), mn = fminf(fabsf(fr), fabsf(fi));
+  const float q = __fdividef(mn, mx);
+  const float iga = __frcp_rn(mx * sqrtf(fmaf(q, q, 1.0f)));  // 1 / |g| (scaled)
+  const float az = 0.5f * fabsf(fd) * iga;                     // |zeta| = |aj - ai| / (2 |g|)
+  float t = az > 1e15f ? __fdividef(0.5f, az) : __frcp_rn(az + sqrtf(fmaf(az, az, 1.0f)));
+  t = copysignf(t, fd);
+  const double tr = (double)(t * (fr * iga)), ti = (double)(t * (fi * iga));  // tau = t (g / |g|): unit phase first, t alone can be 1e-30
+  const double t2 = fma(tr, tr, ti * ti);
+  r.cs = rsqrt(1.0 + t2);
+  r.sr = r.cs * tr;
+  r.si = r.cs * ti;
+  const double c2 = r.cs * r.cs;
+  const double cross = 2.0 * fma(tr, gr, ti * gi);  // 2 Re(conj(tau) g)
+  r.ni = c2 * (ai - cross + t2 * aj);
+  r.nj = c2 * (aj + cross + t2 * ai);
   return true;
 }
 
@@ -83,93 +114,119 @@ __device__ __forceinline__ void rot_apply(cplx &u, cplx &v, const Rot &r) {
   v = vn;
 }
 
+__device__ __forceinline__ void warp_sum2(double &a, double &b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+}
+
 // both rows in shared memory (internal pairs of a block)
-template <int NPL>
+template <int NPL, bool FULL>
 __device__ __forceinline__ int pair_smem(cplx *xi, cplx *xj, int N, int lane, double *ni, double *nj, double dead,
-                                         double tol2) {
+                                         double tol2, int rot64) {
   const double ai = *ni, aj = *nj;
   if (ai <= dead || aj <= dead) return 0;
   cplx u[NPL], v[NPL];
-  double gr = 0.0, gi = 0.0;
+  double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
 #pragma unroll
   for (int e = 0; e < NPL; ++e) {
     const int c = lane + 32 * e;
-    u[e] = c < N ? xi[c] : cmake(0.0, 0.0);
-    v[e] = c < N ? xj[c] : cmake(0.0, 0.0);
-    gr = fma(u[e].x, v[e].x, gr);
-    gr = fma(u[e].y, v[e].y, gr);
-    gi = fma(u[e].y, v[e].x, gi);
-    gi = fma(-u[e].x, v[e].y, gi);
+    u[e] = (FULL || c < N) ? xi[c] : cmake(0.0, 0.0);
+    v[e] = (FULL || c < N) ? xj[c] : cmake(0.0, 0.0);
+    g0 = fma(u[e].x, v[e].x, g0);
+    g1 = fma(u[e].y, v[e].y, g1);
+    h0 = fma(u[e].y, v[e].x, h0);
+    h1 = fma(-u[e].x, v[e].y, h1);
   }
-  gr = tcj::warp_sum(gr);
-  gi = tcj::warp_sum(gi);
+  double gr = g0 + g1, gi = h0 + h1;
+  warp_sum2(gr, gi);
   Rot r;
-  if (!make_rot(ai, aj, gr, gi, tol2, r)) return 0;
+  if (!make_rot(ai, aj, gr, gi, tol2, r, rot64)) return 0;
+  const int big = (gr * gr + gi * gi) > tcj::SMALL_REL2 * ai * aj;
 #pragma unroll
   for (int e = 0; e < NPL; ++e) {
     const int c = lane + 32 * e;
     rot_apply(u[e], v[e], r);
-    if (c < N) {
+    if (FULL || c < N) {
       xi[c] = u[e];
       xj[c] = v[e];
     }
   }
   if (lane == 0) {
-    *ni = ai - r.tg;
-    *nj = aj + r.tg;
+    *ni = r.ni;
+    *nj = r.nj;
   }
-  return 1;
+  return big;
 }
 
 // row i in registers (u), row j in shared memory
-template <int NPL>
+template <int NPL, bool FULL>
 __device__ __forceinline__ int pair_reg(cplx (&u)[NPL], cplx *xj, int N, int lane, double *ni, double *nj, double dead,
-                                        double tol2) {
+                                        double tol2, int rot64) {
   const double ai = *ni, aj = *nj;
   if (ai <= dead || aj <= dead) return 0;
   cplx v[NPL];
-  double gr = 0.0, gi = 0.0;
+  double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
 #pragma unroll
   for (int e = 0; e < NPL; ++e) {
     const int c = lane + 32 * e;
-    v[e] = c < N ? xj[c] : cmake(0.0, 0.0);
-    gr = fma(u[e].x, v[e].x, gr);
-    gr = fma(u[e].y, v[e].y, gr);
-    gi = fma(u[e].y, v[e].x, gi);
-    gi = fma(-u[e].x, v[e].y, gi);
+    v[e] = (FULL || c < N) ? xj[c] : cmake(0.0, 0.0);
+    g0 = fma(u[e].x, v[e].x, g0);
+    g1 = fma(u[e].y, v[e].y, g1);
+    h0 = fma(u[e].y, v[e].x, h0);
+    h1 = fma(-u[e].x, v[e].y, h1);
   }
-  gr = tcj::warp_sum(gr);
-  gi = tcj::warp_sum(gi);
+  double gr = g0 + g1, gi = h0 + h1;
+  warp_sum2(gr, gi);
   Rot r;
-  if (!make_rot(ai, aj, gr, gi, tol2, r)) return 0;
+  if (!make_rot(ai, aj, gr, gi, tol2, r, rot64)) return 0;
+  const int big = (gr * gr + gi * gi) > tcj::SMALL_REL2 * ai * aj;
 #pragma unroll
   for (int e = 0; e < NPL; ++e) {
     const int c = lane + 32 * e;
     rot_apply(u[e], v[e], r);
-    if (c < N) xj[c] = v[e];
+    if (FULL || c < N) xj[c] = v[e];
   }
   if (lane == 0) {
-    *ni = ai - r.tg;
-    *nj = aj + r.tg;
+    *ni = r.ni;
+    *nj = r.nj;
   }
-  return 1;
+  return big;
 }
 
 struct Stage {
   cplx *P, *Q[2];
   double *nrm2;
+  int *ver;  // [2][BR] hand-over counters of the rows in Q[0], Q[1]
   uint64_t *barP, *barQ;  // barQ[2]
 };
 
-template <int NPL>
-__device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, const Stage &st, int *s_rot,
-                       double *red) {
+template <int NPL, bool FULL>
+__device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int *s_rot, double *red) {
+  // carve the stage out of dynamic shared memory here so that the compiler keeps the shared address space
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Stage st;
+  st.P = reinterpret_cast<cplx *>(smem_raw);
+  st.Q[0] = st.P + (size_t)BR * N;
+  st.Q[1] = st.Q[0] + (size_t)BR * N;
+  {
+    unsigned char *tail = smem_raw + (size_t)3 * BR * d.n2 * sizeof(cplx);
+    st.nrm2 = reinterpret_cast<double *>(tail);
+    st.barP = reinterpret_cast<uint64_t *>(tail + d.n2 * sizeof(double));
+    st.barQ = st.barP + 1;
+    st.ver = reinterpret_cast<int *>(st.barP + 4);
+  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nblk = (K + BR - 1) / BR;
   const double tol = 2.0 * sqrt((double)N) * 2.220446049250313e-16;
   const double tol2 = tol * tol;
   const uint32_t row_bytes = (uint32_t)N * sizeof(cplx);
   uint32_t phP = 0, phQ[2] = {0, 0};
+  int verBase[2] = {0, 0};
+  const int rot64 = d.rot64 & 1;
+  const bool lockstep = (d.rot64 & 2) != 0;
   double dead = 0.0;
   int sweep = 0;
   for (; sweep < tcj::MAX_SWEEPS; ++sweep) {
@@ -211,8 +268,8 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, con
         if (warp < rowsP / 2) {
           int i, j;
           tcj::rr_pair(rowsP, r, warp, i, j);
-          nrot += pair_smem<NPL>(st.P + (size_t)i * N, st.P + (size_t)j * N, N, lane, st.nrm2 + p * BR + i,
-                                 st.nrm2 + p * BR + j, dead, tol2);
+          nrot += pair_smem<NPL, FULL>(st.P + (size_t)i * N, st.P + (size_t)j * N, N, lane, st.nrm2 + p * BR + i,
+                                 st.nrm2 + p * BR + j, dead, tol2, rot64);
         }
         __syncthreads();
       }
@@ -222,7 +279,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, con
 #pragma unroll
       for (int e = 0; e < NPL; ++e) {
         const int c = lane + 32 * e;
-        u[e] = (haveP && c < N) ? st.P[(size_t)warp * N + c] : cmake(0.0, 0.0);
+        u[e] = (haveP && (FULL || c < N)) ? st.P[(size_t)warp * N + c] : cmake(0.0, 0.0);
       }
       // ---- every later block streams through Q
       for (int q = p + 1; q < nblk; ++q) {
@@ -237,14 +294,42 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, con
         mbar_wait(&st.barQ[buf], phQ[buf]);
         phQ[buf] ^= 1;
         cplx *Q = st.Q[buf];
-        for (int s = 0; s < BR; ++s) {
-          const int jq = (warp + s) & (BR - 1);
-          if (haveP && jq < rowsQ)
-            nrot += pair_reg<NPL>(u, Q + (size_t)jq * N, N, lane, st.nrm2 + p * BR + warp, st.nrm2 + q * BR + jq, dead,
-                                  tol2);
-          if (s == BR - 1) fence_async_smem();
-          __syncthreads();
+        if (lockstep) {
+          for (int s = 0; s < BR; ++s) {
+            const int jq = (warp + s) & (BR - 1);
+            if (haveP && jq < rowsQ)
+              nrot += pair_reg<NPL, FULL>(u, Q + (size_t)jq * N, N, lane, st.nrm2 + p * BR + warp,
+                                          st.nrm2 + q * BR + jq, dead, tol2, rot64);
+            __syncthreads();
+          }
+        } else {
+          // point-to-point hand-over: row jq carries a version counter; round s of this visit may touch it
+          // once rounds 0..s-1 have released it (the previous holder is warp w+1).  No CTA-wide barrier
+          // inside the visit, so the warps drift apart and one warp's scalar rotation set-up overlaps the
+          // FP64-heavy dot / rotate phases of the others.
+          const uint32_t vaddr = smem_u32(st.ver + buf * BR);
+          const int base = verBase[buf];
+          for (int s = 0; s < BR; ++s) {
+            const int jq = (warp + s) & (BR - 1);
+            if (s > 0) {
+              int v;
+              unsigned long long spins = 0;
+              do {
+                asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(vaddr + 4 * jq) : "memory");
+                if (++spins > (1ull << 24)) __trap();
+              } while (v < base + s);
+            }
+            if (haveP && jq < rowsQ)
+              nrot += pair_reg<NPL, FULL>(u, Q + (size_t)jq * N, N, lane, st.nrm2 + p * BR + warp,
+                                          st.nrm2 + q * BR + jq, dead, tol2, rot64);
+            __syncwarp();
+            if (lane == 0)
+              asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(vaddr + 4 * jq), "r"(base + s + 1) : "memory");
+          }
+          verBase[buf] = base + BR;
         }
+        fence_async_smem();
+        __syncthreads();
         if (tid == 0) bulk_store(X + (size_t)q * BR * N, Q, rowsQ * row_bytes);
       }
       // ---- block p back to global
@@ -252,7 +337,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, con
 #pragma unroll
         for (int e = 0; e < NPL; ++e) {
           const int c = lane + 32 * e;
-          if (c < N) st.P[(size_t)warp * N + c] = u[e];
+          if (FULL || c < N) st.P[(size_t)warp * N + c] = u[e];
         }
       }
       fence_async_smem();
@@ -269,6 +354,10 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, con
     bulk_wait_all();
     if (sweep >= tcj::MAX_SWEEPS) atomicAdd(&d.flags[1], 1);
     atomicMax(&d.flags[2], sweep + 1);
+    if (K >= 128) {  // sweep statistics of the large matrices (diagnostics)
+      atomicAdd(&d.flags[3], sweep + 1);
+      atomicAdd(&d.flags[4], 1);
+    }
   }
   __syncthreads();
   double *w = d.ww + b.slot * d.n2;
@@ -288,31 +377,27 @@ __global__ void __launch_bounds__(NT, 1) jacobi_blocked_kernel(TcDev d, LayerArg
   const int N = b.N, K = b.M < b.N ? b.M : b.N;
   cplx *X = d.Xw + b.slot * d.slot_stride;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  Stage st;
-  st.P = reinterpret_cast<cplx *>(smem_raw);
-  st.Q[0] = st.P + (size_t)BR * N;
-  st.Q[1] = st.Q[0] + (size_t)BR * N;
-  unsigned char *tail = smem_raw + (size_t)3 * BR * d.n2 * sizeof(cplx);
-  st.nrm2 = reinterpret_cast<double *>(tail);
-  st.barP = reinterpret_cast<uint64_t *>(tail + d.n2 * sizeof(double));
-  st.barQ = st.barP + 1;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)3 * BR * d.n2 * sizeof(cplx) + d.n2 * sizeof(double));
   __shared__ double red[32];
   __shared__ int s_rot;
   if (threadIdx.x == 0) {
-    mbar_init(st.barP, 1);
-    mbar_init(&st.barQ[0], 1);
-    mbar_init(&st.barQ[1], 1);
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
     fence_async_smem();
   }
+  if (threadIdx.x < 2 * BR) reinterpret_cast<int *>(bars + 4)[threadIdx.x] = 0;
   __syncthreads();
   const int npl = (N + 31) / 32;
-  if (npl <= 1)
-    sweeps<1>(d, b, X, K, N, st, &s_rot, red);
+  if (N == 256)
+    sweeps<8, true>(d, b, X, K, N, &s_rot, red);
+  else if (npl <= 1)
+    sweeps<1, false>(d, b, X, K, N, &s_rot, red);
   else if (npl <= 2)
-    sweeps<2>(d, b, X, K, N, st, &s_rot, red);
+    sweeps<2, false>(d, b, X, K, N, &s_rot, red);
   else if (npl <= 4)
-    sweeps<4>(d, b, X, K, N, st, &s_rot, red);
+    sweeps<4, false>(d, b, X, K, N, &s_rot, red);
   else
-    sweeps<8>(d, b, X, K, N, st, &s_rot, red);
+    sweeps<8, false>(d, b, X, K, N, &s_rot, red);
 }
 }  // namespace tcb

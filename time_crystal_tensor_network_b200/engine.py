@@ -102,7 +102,8 @@ class Context:
     def flags(self):
         out = np.zeros(4, dtype=np.int32)
         check(self.lib.tc_get_flags(self._h, iptr(out)), 'tc_get_flags')
-        return {'chi_cap_overflow': int(out[0]), 'svd_not_converged': int(out[1]), 'max_sweeps': int(out[2])}
+        return {'chi_cap_overflow': int(out[0]), 'svd_not_converged': int(out[1]), 'max_sweeps': int(out[2]),
+                'mean_sweeps_large': out[3] / 100.0}
 
     # ------------------------------------------------------------------ model
     def set_model(self, gates, kick):
