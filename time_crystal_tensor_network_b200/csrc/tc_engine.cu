@@ -953,6 +953,18 @@ int tc_dbg_get(tc_ctx *c, int which, int r, int jb, void *out_host, size_t bytes
   return 0;
 }
 
+#ifdef TCB_TIMING
+int tc_dbg_timing(unsigned long long *out8, int reset) {
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpyFromSymbol(out8, tcb::g_tcb_timing, 8 * sizeof(unsigned long long)));
+  if (reset) {
+    unsigned long long z[8] = {0};
+    CK(cudaMemcpyToSymbol(tcb::g_tcb_timing, z, sizeof(z)));
+  }
+  return 0;
+}
+#endif
+
 int tc_probe_fp64(int device, int use_dmma, double *gflops_out) {
   CK(cudaSetDevice(device));
   cudaDeviceProp prop;

@@ -14,7 +14,11 @@
 #include "tc_jacobi.cuh"
 
 namespace tcb {
-constexpr int NW = 16, NT = NW * 32, BR = 16;
+#ifndef TCB_BR
+#define TCB_BR 16
+#endif
+constexpr int NW = TCB_BR, NT = NW * 32, BR = TCB_BR;  // one warp per row of a block
+constexpr int CTAS_PER_SM = BR == 16 ? 1 : 2;
 constexpr int MAX_N = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -52,6 +56,17 @@ __device__ __forceinline__ void bulk_store(void *gmem_dst, const void *smem_src,
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+#ifdef TCB_TIMING
+// phase timers (diagnostic build only): [0] load+dot, [1] warp reduction, [2] rotation set-up, [3] rotate+store,
+// [4] hand-over wait / barrier, [5] pairs rotated, [6] pairs visited, [7] whole kernel (warp 0 of K=256 matrices)
+__device__ unsigned long long g_tcb_timing[8];
+#define TCB_T(var) const long long var = clock64()
+#define TCB_ACC(k, a, b) tacc[k] += (b) - (a)
+#else
+#define TCB_T(var)
+#define TCB_ACC(k, a, b)
+#endif
+
 struct Rot {
   double cs, sr, si, ni, nj;  // cos, s*e (complex), new squared norms
 };
@@ -66,17 +81,21 @@ __device__ __forceinline__ bool make_rot(double ai, double aj, double gr, double
                                          int rot64) {
   const double g2 = gr * gr + gi * gi;
   if (!(g2 > tol2 * ai * aj)) return false;
-  if (rot64) {  // all-FP64 angle (A/B switch TC_ROT64=1)
-    const double rg = rsqrt(g2), ga = g2 * rg;
+  if (rot64) {
+    // FP64 set-up with two rsqrt and no division / sqrt / |g| (default).  With dd = aj - ai and
+    // 2r = sqrt(dd^2 + 4|g|^2):  c^2 = 1/2 + |dd|/(4r),  s e = sign(dd) g / (2 r c),
+    // t|g| = s|g|/c = sign(dd) |g|^2 / (2 r c^2)  (the amount of squared norm that moves between the rows).
     const double dd = aj - ai;
-    const double h = sqrt(fma(dd, dd, 4.0 * g2));
-    const double t = copysign(2.0 * ga / (fabs(dd) + h), dd);
-    r.cs = rsqrt(fma(t, t, 1.0));
-    const double sn = r.cs * t;
-    r.sr = sn * gr * rg;
-    r.si = sn * gi * rg;
-    r.ni = ai - t * ga;
-    r.nj = aj + t * ga;
+    const double rinv = rsqrt(fma(dd, dd, 4.0 * g2));  // 1 / (2r)
+    const double c2 = fma(0.5 * fabs(dd), rinv, 0.5);
+    const double cinv = rsqrt(c2);
+    r.cs = c2 * cinv;
+    const double ks = copysign(rinv * cinv, dd);
+    r.sr = ks * gr;
+    r.si = ks * gi;
+    const double tg = g2 * ks * cinv;
+    r.ni = ai - tg;
+    r.nj = aj + tg;
     return true;
   }
   // scale by an exact power of two so that max(ai, aj) is O(1) in float
@@ -164,9 +183,14 @@ __device__ __forceinline__ int pair_smem(cplx *xi, cplx *xj, int N, int lane, do
 // row i in registers (u), row j in shared memory
 template <int NPL, bool FULL>
 __device__ __forceinline__ int pair_reg(cplx (&u)[NPL], cplx *xj, int N, int lane, double *ni, double *nj, double dead,
-                                        double tol2, int rot64) {
+                                        double tol2, int rot64
+#ifdef TCB_TIMING
+                                        , long long (&tacc)[8]
+#endif
+) {
   const double ai = *ni, aj = *nj;
   if (ai <= dead || aj <= dead) return 0;
+  TCB_T(t0);
   cplx v[NPL];
   double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
 #pragma unroll
@@ -179,10 +203,18 @@ __device__ __forceinline__ int pair_reg(cplx (&u)[NPL], cplx *xj, int N, int lan
     h1 = fma(-u[e].x, v[e].y, h1);
   }
   double gr = g0 + g1, gi = h0 + h1;
+  TCB_T(t1);
   warp_sum2(gr, gi);
+  TCB_T(t2);
+  TCB_ACC(0, t0, t1);
+  TCB_ACC(1, t1, t2);
+#ifdef TCB_TIMING
+  tacc[6] += 1;
+#endif
   Rot r;
   if (!make_rot(ai, aj, gr, gi, tol2, r, rot64)) return 0;
   const int big = (gr * gr + gi * gi) > tcj::SMALL_REL2 * ai * aj;
+  TCB_T(t3);
 #pragma unroll
   for (int e = 0; e < NPL; ++e) {
     const int c = lane + 32 * e;
@@ -193,38 +225,39 @@ __device__ __forceinline__ int pair_reg(cplx (&u)[NPL], cplx *xj, int N, int lan
     *ni = r.ni;
     *nj = r.nj;
   }
+  TCB_T(t4);
+  TCB_ACC(2, t2, t3);
+  TCB_ACC(3, t3, t4);
+#ifdef TCB_TIMING
+  tacc[5] += 1;
+#endif
   return big;
 }
-
-struct Stage {
-  cplx *P, *Q[2];
-  double *nrm2;
-  int *ver;  // [2][BR] hand-over counters of the rows in Q[0], Q[1]
-  uint64_t *barP, *barQ;  // barQ[2]
-};
 
 template <int NPL, bool FULL>
 __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int *s_rot, double *red) {
   // carve the stage out of dynamic shared memory here so that the compiler keeps the shared address space
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  Stage st;
-  st.P = reinterpret_cast<cplx *>(smem_raw);
-  st.Q[0] = st.P + (size_t)BR * N;
-  st.Q[1] = st.Q[0] + (size_t)BR * N;
-  {
-    unsigned char *tail = smem_raw + (size_t)3 * BR * d.n2 * sizeof(cplx);
-    st.nrm2 = reinterpret_cast<double *>(tail);
-    st.barP = reinterpret_cast<uint64_t *>(tail + d.n2 * sizeof(double));
-    st.barQ = st.barP + 1;
-    st.ver = reinterpret_cast<int *>(st.barP + 4);
-  }
+  // plain pointers computed from the shared array (no struct / array of pointers: an indexed pointer
+  // array degrades the accesses to generic LD/ST)
+  cplx *const sP = reinterpret_cast<cplx *>(smem_raw);
+  cplx *const sQ = sP + (size_t)BR * N;  // Q[buf] = sQ + buf * BR * N
+  unsigned char *const tail = smem_raw + (size_t)3 * BR * d.n2 * sizeof(cplx);
+  double *const s_nrm2 = reinterpret_cast<double *>(tail);
+  uint64_t *const barP = reinterpret_cast<uint64_t *>(tail + d.n2 * sizeof(double));
+  uint64_t *const barQ = barP + 1;
+  int *const s_ver = reinterpret_cast<int *>(barP + 4);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef TCB_TIMING
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long tk0 = clock64();
+#endif
   const int nblk = (K + BR - 1) / BR;
   const double tol = 2.0 * sqrt((double)N) * 2.220446049250313e-16;
   const double tol2 = tol * tol;
   const uint32_t row_bytes = (uint32_t)N * sizeof(cplx);
-  uint32_t phP = 0, phQ[2] = {0, 0};
-  int verBase[2] = {0, 0};
+  uint32_t phP = 0, phQ0 = 0, phQ1 = 0;  // scalars, not arrays: dynamic indexing would put them in local memory
+  int verBase0 = 0, verBase1 = 0;
   const int rot64 = d.rot64 & 1;
   const bool lockstep = (d.rot64 & 2) != 0;
   double dead = 0.0;
@@ -238,13 +271,13 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
       double s = 0.0;
       for (int c = lane; c < N; c += 32) s += cabs2(__ldcg(reinterpret_cast<const double2 *>(row + c)));
       s = tcj::warp_sum(s);
-      if (lane == 0) st.nrm2[r] = s;
+      if (lane == 0) s_nrm2[r] = s;
     }
     if (tid == 0) *s_rot = 0;
     __syncthreads();
     if (sweep == 0) {
       double p = 0.0;
-      for (int r = tid; r < K; r += NT) p += st.nrm2[r];
+      for (int r = tid; r < K; r += NT) p += s_nrm2[r];
       dead = tcj::DEAD_REL2 * block_sum(p, red);
     }
     int nrot = 0;
@@ -253,25 +286,44 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
       cplx *gP = X + (size_t)p * BR * N;
       if (tid == 0) {
         bulk_wait_all();  // the previous stores out of P / Q have finished reading shared memory
-        mbar_expect_tx(st.barP, rowsP * row_bytes);
-        bulk_load(st.P, gP, rowsP * row_bytes, st.barP);
+        mbar_expect_tx(barP, rowsP * row_bytes);
+        bulk_load(sP, gP, rowsP * row_bytes, barP);
         if (p + 1 < nblk) {
           const int rq = min(BR, K - (p + 1) * BR);
-          mbar_expect_tx(&st.barQ[0], rq * row_bytes);
-          bulk_load(st.Q[0], X + (size_t)(p + 1) * BR * N, rq * row_bytes, &st.barQ[0]);
+          mbar_expect_tx(&barQ[0], rq * row_bytes);
+          bulk_load(sQ, X + (size_t)(p + 1) * BR * N, rq * row_bytes, &barQ[0]);
         }
       }
-      mbar_wait(st.barP, phP);
+      mbar_wait(barP, phP);
       phP ^= 1;
-      // ---- internal pairs of block p: circle method on rowsP (even) rows, warps 0 .. rowsP/2-1
-      for (int r = 0; r < rowsP - 1; ++r) {
-        if (warp < rowsP / 2) {
-          int i, j;
-          tcj::rr_pair(rowsP, r, warp, i, j);
-          nrot += pair_smem<NPL, FULL>(st.P + (size_t)i * N, st.P + (size_t)j * N, N, lane, st.nrm2 + p * BR + i,
-                                 st.nrm2 + p * BR + j, dead, tol2, rot64);
+      // ---- internal pairs: circle method on the rows of a block, one pair per warp, BR/2 warps per block.
+      // Blocks are handled two at a time (p even: block p in P on warps 0..BR/2-1 and block p+1, already
+      // prefetched into stage 0, on warps BR/2..BR-1) so that no warp idles; any order of the pairs within a
+      // sweep is a valid cyclic Jacobi ordering.
+      bool q0_ready = false;
+      if ((p & 1) == 0) {
+        const bool pairUp = p + 1 < nblk;
+        const int rowsN = pairUp ? min(BR, K - (p + 1) * BR) : 0;
+        if (pairUp) {
+          mbar_wait(&barQ[0], phQ0);
+          phQ0 ^= 1;
+          q0_ready = true;
         }
-        __syncthreads();
+        const int half = warp >= BR / 2;
+        const int wl = warp - half * (BR / 2);
+        const int rowsB = half ? rowsN : rowsP;
+        cplx *blk = half ? sQ : sP;
+        double *nb = s_nrm2 + (p + half) * BR;
+        const int rmax = max(rowsP, rowsN) - 1;
+        for (int r = 0; r < rmax; ++r) {
+          if (r < rowsB - 1 && wl < rowsB / 2) {
+            int i, j;
+            tcj::rr_pair(rowsB, r, wl, i, j);
+            nrot += pair_smem<NPL, FULL>(blk + (size_t)i * N, blk + (size_t)j * N, N, lane, nb + i, nb + j, dead, tol2,
+                                         rot64);
+          }
+          __syncthreads();
+        }
       }
       // ---- row p_w into registers
       cplx u[NPL];
@@ -279,38 +331,58 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
 #pragma unroll
       for (int e = 0; e < NPL; ++e) {
         const int c = lane + 32 * e;
-        u[e] = (haveP && (FULL || c < N)) ? st.P[(size_t)warp * N + c] : cmake(0.0, 0.0);
+        u[e] = (haveP && (FULL || c < N)) ? sP[(size_t)warp * N + c] : cmake(0.0, 0.0);
       }
       // ---- every later block streams through Q
       for (int q = p + 1; q < nblk; ++q) {
         const int buf = (q - p - 1) & 1;
         const int rowsQ = min(BR, K - q * BR);
-        if (tid == 0 && q + 1 < nblk) {
-          bulk_wait_all();  // store of block q-1 (out of Q[buf^1]) complete
-          const int rq = min(BR, K - (q + 1) * BR);
-          mbar_expect_tx(&st.barQ[buf ^ 1], rq * row_bytes);
-          bulk_load(st.Q[buf ^ 1], X + (size_t)(q + 1) * BR * N, rq * row_bytes, &st.barQ[buf ^ 1]);
+        // the prefetch of block q+1 is issued in the middle of this visit (round BR/2): by then the store
+        // of block q-1 out of the other stage has long completed, so its wait costs nothing
+        auto prefetch_next = [&]() {
+          if (tid == 0 && q + 1 < nblk) {
+            bulk_wait_all();
+            const int rq = min(BR, K - (q + 1) * BR);
+            mbar_expect_tx(&barQ[buf ^ 1], rq * row_bytes);
+            bulk_load((sQ + (size_t)(buf ^ 1) * BR * N), X + (size_t)(q + 1) * BR * N, rq * row_bytes,
+                      &barQ[buf ^ 1]);
+          }
+        };
+        if (!(q == p + 1 && q0_ready)) {  // stage 0 of the first visit may already have been consumed above
+          mbar_wait(&barQ[buf], buf ? phQ1 : phQ0);
+          if (buf)
+            phQ1 ^= 1;
+          else
+            phQ0 ^= 1;
         }
-        mbar_wait(&st.barQ[buf], phQ[buf]);
-        phQ[buf] ^= 1;
-        cplx *Q = st.Q[buf];
+        cplx *Q = (sQ + (size_t)buf * BR * N);
         if (lockstep) {
           for (int s = 0; s < BR; ++s) {
+            if (s == BR / 2) prefetch_next();
             const int jq = (warp + s) & (BR - 1);
             if (haveP && jq < rowsQ)
-              nrot += pair_reg<NPL, FULL>(u, Q + (size_t)jq * N, N, lane, st.nrm2 + p * BR + warp,
-                                          st.nrm2 + q * BR + jq, dead, tol2, rot64);
+              nrot += pair_reg<NPL, FULL>(u, Q + (size_t)jq * N, N, lane, s_nrm2 + p * BR + warp,
+                                          s_nrm2 + q * BR + jq, dead, tol2, rot64
+#ifdef TCB_TIMING
+                                          , tacc
+#endif
+              );
+            TCB_T(tb0);
             __syncthreads();
+            TCB_T(tb1);
+            TCB_ACC(4, tb0, tb1);
           }
         } else {
           // point-to-point hand-over: row jq carries a version counter; round s of this visit may touch it
           // once rounds 0..s-1 have released it (the previous holder is warp w+1).  No CTA-wide barrier
           // inside the visit, so the warps drift apart and one warp's scalar rotation set-up overlaps the
           // FP64-heavy dot / rotate phases of the others.
-          const uint32_t vaddr = smem_u32(st.ver + buf * BR);
-          const int base = verBase[buf];
+          const uint32_t vaddr = smem_u32(s_ver + buf * BR);
+          const int base = buf ? verBase1 : verBase0;
           for (int s = 0; s < BR; ++s) {
+            if (s == BR / 2) prefetch_next();
             const int jq = (warp + s) & (BR - 1);
+            TCB_T(tw0);
             if (s > 0) {
               int v;
               unsigned long long spins = 0;
@@ -319,14 +391,23 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
                 if (++spins > (1ull << 24)) __trap();
               } while (v < base + s);
             }
+            TCB_T(tw1);
+            TCB_ACC(4, tw0, tw1);
             if (haveP && jq < rowsQ)
-              nrot += pair_reg<NPL, FULL>(u, Q + (size_t)jq * N, N, lane, st.nrm2 + p * BR + warp,
-                                          st.nrm2 + q * BR + jq, dead, tol2, rot64);
+              nrot += pair_reg<NPL, FULL>(u, Q + (size_t)jq * N, N, lane, s_nrm2 + p * BR + warp,
+                                          s_nrm2 + q * BR + jq, dead, tol2, rot64
+#ifdef TCB_TIMING
+                                          , tacc
+#endif
+              );
             __syncwarp();
             if (lane == 0)
               asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(vaddr + 4 * jq), "r"(base + s + 1) : "memory");
           }
-          verBase[buf] = base + BR;
+          if (buf)
+            verBase1 = base + BR;
+          else
+            verBase0 = base + BR;
         }
         fence_async_smem();
         __syncthreads();
@@ -337,12 +418,12 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
 #pragma unroll
         for (int e = 0; e < NPL; ++e) {
           const int c = lane + 32 * e;
-          if (FULL || c < N) st.P[(size_t)warp * N + c] = u[e];
+          if (FULL || c < N) sP[(size_t)warp * N + c] = u[e];
         }
       }
       fence_async_smem();
       __syncthreads();
-      if (tid == 0) bulk_store(gP, st.P, rowsP * row_bytes);
+      if (tid == 0) bulk_store(gP, sP, rowsP * row_bytes);
     }
     if (lane == 0 && nrot) atomicAdd(s_rot, nrot);
     __syncthreads();
@@ -350,6 +431,12 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
     __syncthreads();
     if (tot == 0) break;
   }
+#ifdef TCB_TIMING
+  if (K == 256 && N == 256 && warp == 3 && lane == 0) {
+    tacc[7] = clock64() - tk0;
+    for (int k = 0; k < 8; ++k) atomicAdd(&g_tcb_timing[k], (unsigned long long)tacc[k]);
+  }
+#endif
   if (tid == 0) {
     bulk_wait_all();
     if (sweep >= tcj::MAX_SWEEPS) atomicAdd(&d.flags[1], 1);
@@ -371,7 +458,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
 }
 
 // dynamic smem: 3 * BR * n2 cplx (P, Q0, Q1) + n2 doubles + 3 mbarriers (n2 <= MAX_N)
-__global__ void __launch_bounds__(NT, 1) jacobi_blocked_kernel(TcDev d, LayerArgs a) {
+__global__ void __launch_bounds__(NT, CTAS_PER_SM) jacobi_blocked_kernel(TcDev d, LayerArgs a) {
   Bond b;
   if (!get_bond(d, a, blockIdx.x, blockIdx.y, b)) return;
   const int N = b.N, K = b.M < b.N ? b.M : b.N;
