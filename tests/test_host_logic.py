@@ -155,3 +155,41 @@ def test_reference_import_layout():
     out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd='/')
     assert out.returncode == 0, out.stderr
     assert abs(float(out.stdout.split()[0]) + 0.050183952461055) < 1e-16 and out.stdout.split()[1] == '3'
+
+
+def test_main_drivers_host_side(golden, tmp_path):
+    """main.py: config parser on the repo's config.txt and on a temp file, DTC detector and Fourier spectrum
+    against the values the reference's own functions produced (bit-exact)."""
+    sys.path.insert(0, ROOT)
+    import main as m
+    cwd = os.getcwd()
+    os.chdir(ROOT)
+    try:
+        params = m.read_parameters('config.txt')
+    finally:
+        os.chdir(cwd)
+    assert params == golden['config_params']
+    f = tmp_path / 'p.txt'
+    f.write_text('# c\nA = 3\nB = 0.5  # x\nC = [1, 2, 3]\nD = [0.5, 1]\nE = neel\nF = a,b\nG = 1,2\nH = []\nK = 1e-3\n\nbad line\n')
+    p = m.read_parameters(str(f))
+    assert p == {'A': 3, 'B': 0.5, 'C': [1, 2, 3], 'D': [0.5, 1.0], 'E': 'neel', 'F': ['a', 'b'], 'G': [1, 2], 'H': [],
+                 'K': 0.001}
+    os.chdir(str(tmp_path))
+    try:
+        assert m.read_parameters('does_not_exist.txt') == {}
+    finally:
+        os.chdir(cwd)
+    for key, ent in golden['post'].items():
+        name, T = key.split('|T=')
+        period = float(T)
+        s = np.array(golden['series'][name])
+        t = np.arange(len(s)) * period
+        with np.errstate(invalid='ignore', divide='ignore'):
+            assert float(m.stringent_dtc_detection(list(np.abs(s)), list(t), period)) == ent['stringent_dtc_detection']
+        if len(s) > 2:
+            fr, pw = m.calculate_fourier_spectrum(t, s, period)
+            assert np.array_equal(fr, ent['fourier_freqs']) and np.array_equal(pw, ent['fourier_power'])
+            assert int(np.argmax(pw)) == ent['fourier_peak_bin']
+    assert m.stringent_dtc_detection([1.0] * 10, list(range(10)), 2.0) == 0.0
+    bad = m.calculate_phase_point(0.2, 2.0, {})          # missing keys -> swallowed, success=False
+    assert bad['success'] is False and bad['A2T'] == 0.0 and bad['avg_bond_dim'] == 1.0
