@@ -86,15 +86,15 @@ class TEBDEvolution:
         return [scipy.linalg.expm(-1j * dt * op) for name, op in hamiltonian_terms.items()
                 if name != 'single_site_terms']
 
-    def evolve(self, psi_initial: MPS, total_time: float, observe_every: int = 1) -> Tuple[List[MPS], List[float], Dict]:
-        """Second-order Trotter steps exp(-i dt/2 H_even) exp(-i dt H_odd) exp(-i dt/2 H_even);
-        returns (states, times, info) with the reference's info keys (tebd_evolution.py:51-108)."""
-        n_steps = int(total_time / self.dt)
+    def _trotter(self, psi_initial: MPS, n_steps: int, prefactor, observe_every: int, dt: float):
+        """n_steps second-order Trotter steps G_even(dt/2) G_odd(dt) G_even(dt/2) with bond gates
+        expm(prefactor * dt * H_b): prefactor = -1j is real time, -1 is imaginary time (the state is
+        renormalised by every update, so non-unitary gates need no extra care)."""
         terms = self._bond_terms()
         L = psi_initial.L
         if len(terms) != L - 1:
             raise ValueError('need one bond term per nearest-neighbour bond')
-        gates = np.array([scipy.linalg.expm(-1j * self.dt * (0.5 if b % 2 == 0 else 1.0) * h)
+        gates = np.array([scipy.linalg.expm(prefactor * dt * (0.5 if b % 2 == 0 else 1.0) * h)
                           for b, h in enumerate(terms)]).reshape(1, L - 1, 4, 4) if L > 1 else None
         tp = self.trunc_params
         chi_max = int(tp.get('chi_max') or 0)
@@ -116,7 +116,7 @@ class TEBDEvolution:
             psi._touch()
             if step % observe_every == 0:
                 states.append(psi.copy())
-                times.append((step + 1) * self.dt)
+                times.append((step + 1) * dt)
                 bond_dims.append(psi.chi)
                 entropies.append(psi.entanglement_entropy())
                 errs.append(float(psi._ctx.trunc_err()[0]))
@@ -132,7 +132,47 @@ class TEBDEvolution:
             'final_bond_dim': psi.chi,
             'n_steps': n_steps,
         }
+        return states, times, info, psi
+
+    def evolve(self, psi_initial: MPS, total_time: float, observe_every: int = 1) -> Tuple[List[MPS], List[float], Dict]:
+        """Real-time second-order Trotter TEBD under the model's nearest-neighbour Hamiltonian; returns
+        (states, times, info) with the reference's info keys (tebd_evolution.py:51-108)."""
+        states, times, info, _ = self._trotter(psi_initial, int(total_time / self.dt), -1j, observe_every, self.dt)
         return states, times, info
+
+    def imaginary_time_evolution(self, psi_initial: MPS, dts=(0.1, 0.05, 0.02, 0.01), steps_per_dt: int = 100) -> Tuple[MPS, Dict]:
+        """Ground-state preparation by imaginary-time TEBD (the README's claim, BASELINE config 5): for every dt of
+        the schedule, ``steps_per_dt`` second-order steps of exp(-dt H).  Returns (psi, info) with the energy
+        after every stage (sum of <H_b>)."""
+        psi = psi_initial
+        energies, chis = [], []
+        for dt in dts:
+            _, _, _, psi = self._trotter(psi, steps_per_dt, -1.0, max(steps_per_dt, 1), dt)
+            energies.append(self.energy(psi))
+            chis.append(max(psi.chi) if psi.chi else 1)
+        return psi, {'energies': energies, 'bond_dimensions': chis, 'dts': list(dts)}
+
+    def energy(self, psi: MPS) -> float:
+        """<H> = sum_b <H_b> through the Pauli expansion of every bond term (two-point correlators on the device)."""
+        paulis = [np.eye(2, dtype=complex), np.array([[0, 1], [1, 0]], dtype=complex),
+                  np.array([[0, -1j], [1j, 0]], dtype=complex), np.array([[1, 0], [0, -1]], dtype=complex)]
+        total = 0.0
+        for b, h in enumerate(self._bond_terms()):
+            h4 = h.reshape(2, 2, 2, 2)
+            for ia, pa in enumerate(paulis):
+                for ib, pb in enumerate(paulis):
+                    c = np.einsum('pqrs,rp,sq->', h4, pa, pb) / 4.0        # tr[(pa x pb) H_b] / 4
+                    if abs(c) < 1e-15:
+                        continue
+                    if ia == 0 and ib == 0:
+                        total += c.real
+                    elif ia == 0:
+                        total += (c * psi.expectation_value(pb, sites=[b + 1])[0]).real
+                    elif ib == 0:
+                        total += (c * psi.expectation_value(pa, sites=[b])[0]).real
+                    else:
+                        total += (c * psi.correlation_function(pa, pb, sites1=[b], sites2=[b + 1])[0, 0]).real
+        return float(total)
 
     def real_time_evolution(self, psi_initial: MPS, hamiltonian, total_time: float,
                             observe_every: int = 1) -> Tuple[List[MPS], List[float], Dict]:
