@@ -1,0 +1,131 @@
+"""The assertions of the reference's own suites (tests/test_basic_functionality.py,
+test_physics_validation.py, test_performance.py), restated for pytest and run against the drop-in modules on
+the GPU.  Import paths are the reference's: only <repo>/src is put on sys.path."""
+import os
+import sys
+import time
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'src'))
+sys.path.insert(0, ROOT)
+
+from core.tensor_utils import create_initial_state, pauli_matrices  # noqa: E402
+from core.observables import (calculate_loschmidt_echo, magnetization, staggered_magnetization,  # noqa: E402
+                              extract_subharmonic_amplitude, order_parameter)
+from models.kicked_ising import KickedIsingModel  # noqa: E402
+from dynamics.tebd_evolution import CustomFloquet, TEBDEvolution  # noqa: E402
+
+
+def test_pauli_and_states():
+    p = pauli_matrices()
+    for a in 'XYZ':
+        assert np.allclose(p[a] @ p[a], p['I'])
+    assert np.allclose(p['X'] @ p['Y'] - p['Y'] @ p['X'], 2j * p['Z'])
+    for st in ('all_up', 'all_down', 'neel', 'random'):
+        psi = create_initial_state(6, st)
+        assert psi.L == 6 and abs(psi.norm - 1.0) < 1e-10
+    assert create_initial_state(1, 'all_up').L == 1
+    with pytest.raises(ValueError):
+        create_initial_state(4, 'invalid')
+
+
+def test_model_construction():
+    m = KickedIsingModel(n_sites=4, J=1.0, h_disorder=0.2, tau=1.0, disorder_seed=42)
+    assert m.n_sites == 4 and m.J == 1.0 and m.tau == 1.0
+    assert len(m.h_fields) == 4 and np.all(np.abs(m.h_fields) <= 0.2)
+    assert len(m.ising_gates) == 3 and m.pi_pulse_gate.shape == (2, 2)
+    m2 = KickedIsingModel(n_sites=4, J=1.0, h_disorder=0.2, tau=1.0, disorder_seed=43)
+    assert not np.allclose(m.h_fields, m2.h_fields)
+    t0 = time.time()
+    for s in range(10):
+        KickedIsingModel(8, 1.0, 0.3, 1.0, disorder_seed=s)
+    assert time.time() - t0 < 5.0
+    for h, tau in ((1e-10, 1.0), (10.0, 1.0), (0.2, 1e-3)):
+        mm = KickedIsingModel(4, 1.0, h, tau, disorder_seed=1)
+        assert abs(mm.floquet_step(create_initial_state(4, 'neel')).norm - 1.0) < 1e-8
+
+
+def test_observables_on_product_states():
+    up, dn, neel = (create_initial_state(4, s) for s in ('all_up', 'all_down', 'neel'))
+    assert abs(calculate_loschmidt_echo(up, up) - 1.0) < 1e-10
+    assert abs(calculate_loschmidt_echo(up, dn)) < 1e-10
+    mu, md = magnetization(up, 'z'), magnetization(dn, 'z')
+    assert abs(abs(mu) - 4.0) < 1e-8 and abs(mu + md) < 1e-8
+    assert abs(magnetization(neel, 'z')) < 1e-8
+    assert abs(abs(magnetization(up, 'z', site=0)) - 1.0) < 1e-8
+    assert abs(staggered_magnetization(neel)) > 0.5 and abs(staggered_magnetization(up)) < 1e-8
+    assert isinstance(magnetization(up, 'x'), float) and isinstance(calculate_loschmidt_echo(up, neel), float)
+    assert up.expectation_value('Sz', sites=[0])[0].real == pytest.approx(0.5)
+
+
+def test_evolution_shapes_norms_and_timing():
+    for L, limit in ((8, 0.1), (12, 0.5), (16, 2.0)):
+        m = KickedIsingModel(L, 1.0, 0.3, 1.0, disorder_seed=42)
+        psi = create_initial_state(L, 'neel')
+        m.floquet_step(psi)                                   # first call pays context creation
+        t0 = time.time()
+        out = m.floquet_step(psi)
+        assert time.time() - t0 < limit
+        assert out.L == L and abs(out.norm - 1.0) < 1e-10
+    m = KickedIsingModel(6, 1.0, 0.3, 0.5, disorder_seed=42)
+    psi = create_initial_state(6, 'neel')
+    cur = psi
+    for _ in range(10):
+        cur = m.floquet_step(cur)
+        assert abs(cur.norm - psi.norm) < 1e-8
+    states, times = m.evolve(psi, 10)
+    assert len(states) == 11 and np.allclose(times, [i * 2 * m.tau for i in range(11)])
+    st, tm, info = CustomFloquet(m, {'chi_max': 16, 'svd_min': 1e-12, 'trunc_cut': 1e-8}).evolve_floquet(psi, 5)
+    assert len(st) == 6 and {'wall_time', 'bond_dimensions', 'final_bond_dim'} <= set(info)
+    assert np.allclose(tm, [i * 2 * m.tau for i in range(6)])
+    t5 = time.time(); m.evolve(psi, 5); t5 = time.time() - t5
+    t20 = time.time(); m.evolve(psi, 20); t20 = time.time() - t20
+    assert t20 / max(t5, 1e-3) < 8
+
+
+def test_time_crystal_signatures():
+    m = KickedIsingModel(8, 1.0, 0.25, 1.0, disorder_seed=42)
+    psi0 = create_initial_state(8, 'neel')
+    states, times = m.evolve(psi0, 20)
+    stag = np.array([staggered_magnetization(s) for s in states])
+    le = [calculate_loschmidt_echo(psi0, s) for s in states]
+    assert np.std(stag) > 0.01 and le[-1] > 0.0
+    assert all(-1e-10 <= x <= 1 + 1e-10 for x in le)
+    assert extract_subharmonic_amplitude(np.array(times), stag, 2 * m.tau) > 0.1
+    assert order_parameter(states[-1], [0, 2, 4, 6], [1, 3, 5, 7]) > 0.5
+    dims = []
+    for L in (4, 8, 12):
+        mm = KickedIsingModel(L, 1.0, 0.3, 1.0, disorder_seed=42)
+        _, _, info = CustomFloquet(mm).evolve_floquet(create_initial_state(L, 'neel'), 5)
+        dims.append(info['final_bond_dim'])
+    assert dims == sorted(dims)
+
+
+def test_scaling_ceilings():
+    for L in (16, 20, 24):
+        m = KickedIsingModel(L, 1.0, 0.3, 1.0, disorder_seed=42)
+        t0 = time.time()
+        CustomFloquet(m, {'chi_max': 64, 'svd_min': 1e-12}).evolve_floquet(create_initial_state(L, 'neel'), 5)
+        assert time.time() - t0 < 30
+    m = KickedIsingModel(12, 1.0, 0.3, 1.0, disorder_seed=42)
+    t0 = time.time()
+    m.evolve(create_initial_state(12, 'neel'), 50)
+    assert time.time() - t0 < 60
+    te = TEBDEvolution(m)
+    assert te.evolve_floquet_period(create_initial_state(12, 'neel')).L == 12
+
+
+def test_perfect_dtc_driver_full_size():
+    """basic:454-479 runs simulate_perfect_dtc at its real size (L = 64, 200 periods)."""
+    import main as mm
+    params = {'J': 1.0, 'CHI_MAX': 256, 'SVD_MIN': 1e-12, 'SVD_CUTOFF': 1e-7, 'RANDOM_SEED': 42}
+    t0 = time.time()
+    times, stag, total = mm.simulate_perfect_dtc(params)
+    assert len(times) == len(stag) == len(total) == 201
+    assert all(abs(s) <= 1 + 1e-10 for s in stag) and np.std(stag) > 0.01
+    assert time.time() - t0 < 300
