@@ -168,7 +168,7 @@ def run_reference(a):
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': a.gpus,
         'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'complex128 (f64)', 'data': 'synthetic',
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': workload_name(a), 'note': 'CPU arm: oracle port of the reference TEBD/TeNPy path '
                    '(TeNPy itself is not installable here); one single-threaded process per host core, one chain each'},
         'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
@@ -182,6 +182,20 @@ def run_reference(a):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def ncu_traffic_gb():
+    """DRAM bytes of the dominant kernel from the committed ncu capture (None if the file is missing)."""
+    path = os.path.join(ROOT, 'profiles', 'r01_jacobi_blocked_ncu_metrics.txt')
+    try:
+        tot = 0.0
+        for line in open(path):
+            for key in ('dram__bytes_read.sum [Gbyte] = ', 'dram__bytes_write.sum [Gbyte] = '):
+                if line.startswith(key):
+                    tot += float(line[len(key):])
+        return tot or None
+    except Exception:
+        return None
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -288,7 +302,7 @@ def run_ours(a):
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': ms_max / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'complex128 (f64)', 'data': 'synthetic',
+            'dtype': 'f64', 'data': 'synthetic',
             'config': {'workload': workload_name(a), 'chains_total': world * R, 'L': L, 'chi_max': a.chi,
                        'svds_per_step_per_chain': 2 * (L - 1), 'prep_periods': n_prep, 'prep_eps': a.prep_eps,
                        'prep_s': round(t_prep, 2), 'chi_mid_min': int(chi_now[:, L // 2].min()),
@@ -305,7 +319,9 @@ def run_ours(a):
                 'bound': 'fp64', 'kernel': 'qr_kernel + jacobi_rows_kernel + finalize_kernel (batched truncated SVD)',
                 'achieved': achieved, 'peak': fp64_peak, 'unit': 'TFLOP/s',
                 'frac': (achieved / fp64_peak) if achieved else None,
-                'traffic': None,
+                'traffic': ncu_traffic_gb(),
+                'traffic_unit': 'GB per Jacobi launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full capture '
+                                'of a 32-chain layer, profiles/r01_jacobi_blocked_ncu_metrics.txt); algorithmic: 0.8 GB',
                 'peak_source': 'tc_probe_fp64 (DFMA chain, all SMs) measured in this run; MEASURED_PEAKS.json has no '
                                f'FP64 entry (hbm_gbs={peaks.get("hbm_gbs")}); DMMA probe {dmma_peak:.1f} TFLOP/s',
                 'flops_model': 'SURVEY 8d: 4(4m^2 n + 8 m n^2 + 9 n^3) per update, summed over the actual bond '
