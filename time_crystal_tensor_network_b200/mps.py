@@ -218,6 +218,44 @@ class MPS:
                                                   _as_matrix(op2, self.sites[j]))
         return np.real_if_close(out)
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    def save(self, path):
+        """Write the state (site tensors in 'B' form, Schmidt values, site bookkeeping) to an ``.npz`` file.
+        The reference keeps states only in Python lists (no checkpointing); this is the engine's
+        resume format for long runs."""
+        data = {'L': np.int64(self.L), 'norm': np.float64(self.norm),
+                'conserve': np.array([str(getattr(s, 'conserve', None)) for s in self.sites]),
+                'up': np.array([int(getattr(s, '_up', 0)) for s in self.sites], dtype=np.int64)}
+        for i in range(self.L):
+            data[f'B{i}'] = self.get_B(i, 'B')
+        for b in range(self.L + 1):
+            data[f'S{b}'] = self._ctx.get_S(0, b)
+        np.savez(path, **data)
+
+    @classmethod
+    def load(cls, path, device=0):
+        """Inverse of :meth:`save`."""
+        with np.load(path, allow_pickle=False) as z:
+            L = int(z['L'])
+            Bs = [z[f'B{i}'] for i in range(L)]
+            Ss = [z[f'S{b}'] for b in range(L + 1)]
+            conserve, up, norm = [str(c) for c in z['conserve']], z['up'], float(z['norm'])
+        cap = max(max(b.shape[0], b.shape[2]) for b in Bs)
+        ctx = Context(L, cap, 1, device)
+        for i, b in enumerate(Bs):
+            ctx.set_site(0, i, b)
+        for b, s_ in enumerate(Ss):
+            ctx.set_S(0, b, s_)
+        sites = []
+        for c, u in zip(conserve, up):
+            st = SpinHalfSite(None if c == 'None' else c)
+            st._up = int(u)
+            st.state_labels = {'up': st._up, 'down': 1 - st._up}
+            sites.append(st)
+        out = cls(ctx, sites)
+        out.norm = norm
+        return out
+
     # ------------------------------------------------------------------ misc
     def to_statevector(self):
         """Dense amplitudes (small L; host contraction of downloaded tensors, for tests/debugging)."""
