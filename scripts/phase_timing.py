@@ -1,4 +1,6 @@
-"""Diagnostic: per-phase cycle counters of the blocked Jacobi kernel (library built with -DTCB_TIMING)."""
+"""Diagnostic: per-phase cycle counters of the Jacobi kernels (library built with -DTCB_TIMING as
+libtc_b200_timing.so).  TC_JACOBI=rb (default) reports the register-blocked kernel's phases, TC_JACOBI=blocked the
+16-warp kernel's."""
 import ctypes as C, sys, os
 import numpy as np
 sys.path.insert(0, '.')
@@ -17,10 +19,17 @@ lib.tc_dbg_timing(out, 1)
 ens.ctx.floquet_step(1)
 lib.tc_dbg_timing(out, 1)
 v = np.array(list(out), dtype=float)
-names = ['load+dot', 'warp reduce', 'rotation set-up', 'rotate+store', 'wait/barrier', 'pairs rotated', 'pairs visited', 'kernel total']
-for n, x in zip(names, v):
-    print(f'{n:18s} {x:.4g}')
-print('per visited pair: load+dot %.0f  reduce %.0f  | per rotated pair: setup %.0f  rotate %.0f | wait per visited %.0f' % (
-    v[0] / v[6], v[1] / v[6], v[2] / v[5], v[3] / v[5], v[4] / v[6]))
-print('sum of phases / kernel total = %.2f ; rotated fraction %.2f' % (v[:5].sum() / v[7], v[5] / v[6]))
+if os.environ.get('TC_JACOBI', 'rb') == 'blocked':
+    names = ['load+dot', 'warp reduce', 'rotation set-up', 'rotate+store', 'wait/barrier', 'pairs rotated', 'pairs visited', 'kernel total']
+    for n, x in zip(names, v):
+        print(f'{n:18s} {x:.4g}')
+    print('per visited pair: load+dot %.0f  reduce %.0f  | per rotated pair: setup %.0f  rotate %.0f | wait per visited %.0f' % (
+        v[0] / v[6], v[1] / v[6], v[2] / v[5], v[3] / v[5], v[4] / v[6]))
+    print('sum of phases / kernel total = %.2f ; rotated fraction %.2f' % (v[:5].sum() / v[7], v[5] / v[6]))
+else:
+    names = ['internal phase', 'streaming visits', '  hand-over waits', 'stage wait + barrier', 'P block load wait',
+             '  tournaments', 'visits', 'kernel total']
+    for n, x in zip(names, v):
+        print(f'{n:22s} {x:.4g}  ({100 * x / v[7]:.1f} % of kernel)' if n != 'visits' else f'{n:22s} {x:.4g}')
+    print('cycles per visit %.0f (= %d pairs per warp)' % (v[1] / v[6], 64))
 print(ens.ctx.flags())

@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libtc_b200.so')
+# TC_B200_LIB: another build of the same library (diagnostic / A-B builds); the default is the in-tree one
+LIB_PATH = os.environ.get('TC_B200_LIB') or os.path.join(HERE, 'libtc_b200.so')
 
 TRUNC_REFERENCE = 0
 TRUNC_TEBD = 1
