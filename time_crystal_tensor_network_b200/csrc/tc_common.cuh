@@ -108,6 +108,15 @@ __device__ __forceinline__ bool get_bond(const TcDev &d, const LayerArgs &a, int
   return true;
 }
 
+// Largest matrices first (long SVD kernels): with grid (chains, bonds) the CTAs of bond rank y are scheduled before
+// those of rank y+1; rank 0 is the centre of the chain, so the full-size updates start in the first wave and the
+// small edge bonds fill the tail.
+__device__ __forceinline__ int centre_out(int x, int nb) {
+  const int c = nb / 2;
+  const int k = (x + 1) / 2;
+  return (x & 1) ? c - k : c + k;  // x = 0 -> c, 1 -> c-1, 2 -> c+1, ...: a bijection of [0, nb) for odd and even nb
+}
+
 __device__ __forceinline__ cplx *site_ptr(const TcDev &d, int r, int site) {
   return d.B + ((size_t)r * d.L + site) * d.site_stride;
 }

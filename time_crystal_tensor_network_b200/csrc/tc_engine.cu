@@ -65,7 +65,7 @@ struct tc_ctx {
   bool have_model = false;
   bool blocked_attr_set = false;
   bool rb_attr_set = false;
-  int jacobi_kind = 2;  // TC_JACOBI = rb (2, default: register-blocked) | blocked (1: 16-warp kernel) | simple (0), A/B testing
+  int jacobi_kind = 1;  // TC_JACOBI = blocked (1, default: 16-warp kernel) | rb (2: register-blocked, experimental) | simple (0)
   bool force_simple_jacobi = false;  // TC_JACOBI=simple: the warp-per-pair kernel for every size (A/B testing)
   // record buffers for tc_floquet_run_host
   void *rec = nullptr;
@@ -359,7 +359,7 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
     {
       ProfScope ps(c, TC_PROF_QR);
       if (d.n2 <= tcj::QMAXM && !c->force_simple_jacobi)
-        tcj::qr_blocked_kernel<<<dim3(nb, nr), tcj::QNT, 0, c->stream>>>(d, a);
+        tcj::qr_blocked_kernel<<<dim3(nr, nb), tcj::QNT, 0, c->stream>>>(d, a);
       else
         tcj::qr_kernel<<<dim3(nb, nr), tcj::NT, (d.n2 + 64) * sizeof(cplx), c->stream>>>(d, a);
       LAUNCHED();
@@ -369,21 +369,17 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
       if (d.n2 <= tcr::MAX_N && c->jacobi_kind == 2) {
         const size_t smem = tcr::smem_bytes(d.n2);
         if (!c->rb_attr_set) {
-          CK(cudaFuncSetAttribute(tcr::jacobi_rb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          CK(cudaFuncSetAttribute(tcr::jacobi_rb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          CK(cudaFuncSetAttribute(tcr::jacobi_rb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           c->rb_attr_set = true;
         }
-        // pipelined sweeps while most pairs still rotate, then the skipping sweeps until convergence
-        tcr::jacobi_rb_kernel<true><<<dim3(nr, nb), tcr::NT, smem, c->stream>>>(d, a);
-        LAUNCHED();
-        tcr::jacobi_rb_kernel<false><<<dim3(nr, nb), tcr::NT, smem, c->stream>>>(d, a);
+        tcr::jacobi_rb_kernel<<<dim3(nr, nb), tcr::NT, smem, c->stream>>>(d, a);
       } else if (d.n2 <= tcb::MAX_N && !c->force_simple_jacobi) {
         const size_t smem = (size_t)3 * tcb::BR * d.n2 * sizeof(cplx) + d.n2 * sizeof(double) + 64 + 2 * tcb::BR * sizeof(int);
         if (!c->blocked_attr_set) {
           CK(cudaFuncSetAttribute(tcb::jacobi_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           c->blocked_attr_set = true;
         }
-        tcb::jacobi_blocked_kernel<<<dim3(nb, nr), tcb::NT, smem, c->stream>>>(d, a);
+        tcb::jacobi_blocked_kernel<<<dim3(nr, nb), tcb::NT, smem, c->stream>>>(d, a);
       } else {
         tcj::jacobi_rows_kernel<<<dim3(nb, nr), tcj::NT, d.n2 * sizeof(double), c->stream>>>(d, a);
       }
@@ -493,7 +489,7 @@ int tc_ctx_create(int device, int L, int chi_cap, int R, void *arena, size_t are
   c->arena_bytes = lo.total;
   if (const char *e = getenv("TC_JACOBI")) {
     c->force_simple_jacobi = strcmp(e, "simple") == 0;
-    c->jacobi_kind = strcmp(e, "simple") == 0 ? 0 : (strcmp(e, "blocked") == 0 ? 1 : 2);
+    c->jacobi_kind = strcmp(e, "simple") == 0 ? 0 : (strcmp(e, "rb") == 0 ? 2 : 1);
   }
   if (stream) {
     c->stream = (cudaStream_t)stream;

@@ -176,7 +176,8 @@ __device__ __forceinline__ void block_sum_vec(double (&v)[NV], double *scratch, 
 
 __global__ void __launch_bounds__(QNT) qr_blocked_kernel(TcDev d, LayerArgs a) {
   Bond b;
-  if (!get_bond(d, a, blockIdx.x, blockIdx.y, b)) return;
+  // blockIdx.x = chain, blockIdx.y = rank of the bond in centre-out order (largest matrices first)
+  if (!get_bond(d, a, centre_out(blockIdx.y, a.nb), blockIdx.x, b)) return;
   const int M = b.M, N = b.N;
   cplx *X = d.Xw + b.slot * d.slot_stride;
   __shared__ __align__(16) cplx V[QMAXM * QB];

@@ -460,7 +460,8 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
 // dynamic smem: 3 * BR * n2 cplx (P, Q0, Q1) + n2 doubles + 3 mbarriers (n2 <= MAX_N)
 __global__ void __launch_bounds__(NT, CTAS_PER_SM) jacobi_blocked_kernel(TcDev d, LayerArgs a) {
   Bond b;
-  if (!get_bond(d, a, blockIdx.x, blockIdx.y, b)) return;
+  // blockIdx.x = chain, blockIdx.y = rank of the bond in centre-out order (largest matrices first)
+  if (!get_bond(d, a, centre_out(blockIdx.y, a.nb), blockIdx.x, b)) return;
   const int N = b.N, K = b.M < b.N ? b.M : b.N;
   cplx *X = d.Xw + b.slot * d.slot_stride;
   extern __shared__ __align__(128) unsigned char smem_raw[];

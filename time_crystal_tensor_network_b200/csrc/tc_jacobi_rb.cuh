@@ -1,10 +1,9 @@
-// tc_jacobi_rb.cuh -- K2b fast path, register-blocked: one-sided Jacobi on the rows of the triangular
-// factor with FOUR stationary rows per warp in registers and every streamed row reused four times per
-// shared-memory load.
+// tc_jacobi_rb.cuh -- K2b, register-blocked variant (TC_JACOBI=rb; the 16-warp kernel of tc_jacobi_blocked.cuh is
+// the default): one-sided Jacobi on the rows of the triangular factor with FOUR stationary rows per warp in registers
+// and every streamed row reused four times per shared-memory load.
 //
-// Why (ncu of the 16-warp kernel tc_jacobi_blocked.cuh, profiles/r01_*): one stationary row per warp costs
-// 4 KB LDS + 4 KB STS per row pair, which puts the shared-memory pipe at 52 % while the FP64 pipe sits at 45 %:
-// the two co-limit, and every pair pays its own shuffle reduction and scalar rotation set-up chain.  Here
+// Design (vs ncu of the 16-warp kernel, profiles/r01_*: one stationary row per warp costs 4 KB LDS + 4 KB STS per row
+// pair -- shared-memory pipe 52 %, FP64 pipe 45 %, and every pair pays its own shuffle reduction and set-up chain):
 //   * a CTA of 8 warps (255 registers) holds a P block of 32 rows in registers, 4 per warp; a streamed q row is
 //     loaded once, rotated against the warp's 4 rows and stored once: 2 KB of shared-memory traffic per pair;
 //   * every warp keeps TWO q rows in flight as a wavefront, (p_t, q_a) next to (p_{t-1}, q_b): the two dot
@@ -16,6 +15,15 @@
 // with 2 rows per warp in registers), then all later rows stream through in blocks of 16.
 // Same rotation formulas, thresholds and stopping rule as tc_jacobi_blocked.cuh; only the pair ORDER differs
 // (any order that meets every pair once per sweep is a cyclic Jacobi ordering).
+//
+// Measured (B200, L = 32, chi = 128, 32 chains, one parity layer): 44.9 ms against 42.6 ms for the 16-warp kernel, i.e.
+// the 4x lower shared-memory traffic does not pay: with 2 warps per scheduler the serial chain dot -> shuffle
+// reduction -> set-up -> rotate of a warp is not hidden (scripts/ubench/pair_chain.cu: 120 cycles per row pair
+// per SM with every row in registers, FP64 bound 92).  A software-pipelined visit (A's set-up next to B's rotations
+// fused with the next dot, branch-free) was built and measured slower still (51.7 ms): ptxas keeps the two chains
+// back to back inside the basic block.  Lessons kept here: control values that come from memory go through a REDUX
+// (`uni`) and spin loops exit on a vote, otherwise every later shuffle carries a BRA.DIV divergence check; rsqrt(double)
+// hides a branch, `rsqrt_nb` does not.
 #pragma once
 #include "tc_common.cuh"
 #include "tc_jacobi.cuh"
@@ -47,21 +55,11 @@ constexpr unsigned FULLM = 0xffffffffu;
 // [4] P block load wait, [5] tournaments (part of [0]), [6] visits, [7] whole kernel
 #define TCR_ARG , long long (&tacc)[8]
 #define TCR_PASS , tacc
-#define TCR_ARGP , long long *taccp
-#define TCR_PASSP , tacc
-#define TCR_TACC                                  \
-  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
-#define TCR_TSAVE \
-  for (int k_ = 0; k_ < 8; ++k_) taccp[k_] += tacc[k_]
 #define TCR_T(v) const long long v = clock64()
 #define TCR_ACC(k, a, b) tacc[k] += (b) - (a)
 #else
 #define TCR_ARG
 #define TCR_PASS
-#define TCR_ARGP
-#define TCR_PASSP
-#define TCR_TACC
-#define TCR_TSAVE
 #define TCR_T(v)
 #define TCR_ACC(k, a, b)
 #endif
@@ -227,8 +225,6 @@ __device__ __forceinline__ int pair2(cplx (&uA)[NPL], cplx (&vA)[NPL], double &a
   return (int)rotA | ((int)rotB << 1) | (int)((bbig & 1u) << 2) | (int)(((bbig >> 16) & 1u) << 3);
 }
 __device__ __forceinline__ int nbig(int flags) { return ((flags >> 2) & 1) + ((flags >> 3) & 1); }
-// visits return two counters in one int: bits 0..15 rotations, bits 16..31 rotations that were not yet small
-__device__ __forceinline__ int packfl(int flags) { return (flags & 1) + ((flags >> 1) & 1) + (nbig(flags) << 16); }
 
 __device__ __forceinline__ void ver_release(uint32_t addr, int val, int lane) {
   __syncwarp();
@@ -264,7 +260,7 @@ __device__ __forceinline__ int visit(cplx (&u)[PR][NPL], double (&pn)[PR], unsig
       nA = qn[ja];
     }
     // step 0: (p_0, q_a) with the last pair of the previous slot's q_b
-    nrot += packfl(pair2<NPL>(u[0], vA, pn[0], nA, okA && (pvalid & 1u), u[NP - 1], vB, pn[NP - 1], nB,
+    nrot += nbig(pair2<NPL>(u[0], vA, pn[0], nA, okA && (pvalid & 1u), u[NP - 1], vB, pn[NP - 1], nB,
                        s > 0 && okB && ((pvalid >> (NP - 1)) & 1u), dead, tol2, lane));
     if (s > 0) {
       if (okB) {
@@ -285,7 +281,7 @@ __device__ __forceinline__ int visit(cplx (&u)[PR][NPL], double (&pn)[PR], unsig
     }
 #pragma unroll
     for (int t = 1; t < NP; ++t)
-      nrot += packfl(pair2<NPL>(u[t], vA, pn[t], nA, okA && ((pvalid >> t) & 1u), u[t - 1], vB, pn[t - 1], nB,
+      nrot += nbig(pair2<NPL>(u[t], vA, pn[t], nA, okA && ((pvalid >> t) & 1u), u[t - 1], vB, pn[t - 1], nB,
                          okB && ((pvalid >> (t - 1)) & 1u), dead, tol2, lane));
     if (okA) {
       st_row<NPL, FULL>(vA, Q + (size_t)ja * N, N, lane);
@@ -297,7 +293,7 @@ __device__ __forceinline__ int visit(cplx (&u)[PR][NPL], double (&pn)[PR], unsig
   // drain: the last pair of the last q_b
   {
     double dumA = 0.0, dumB = 0.0;
-    nrot += packfl(pair2<NPL>(u[0], vA, dumA, dumB, false, u[NP - 1], vB, pn[NP - 1], nB,
+    nrot += nbig(pair2<NPL>(u[0], vA, dumA, dumB, false, u[NP - 1], vB, pn[NP - 1], nB,
                        okB && ((pvalid >> (NP - 1)) & 1u), dead, tol2, lane));
     if (okB) {
       st_row<NPL, FULL>(vB, Q + (size_t)jb_prev * N, N, lane);
@@ -306,168 +302,6 @@ __device__ __forceinline__ int visit(cplx (&u)[PR][NPL], double (&pn)[PR], unsig
     ver_release(vaddr + 4 * jb_prev, base + NW, lane);
   }
   return nrot;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Software-pipelined visit (NP >= 3).  The lock-step visit above leaves the FP64 pipe idle while a warp walks
-// through its serial chain dot -> shuffle reduction -> rotation set-up (~400 cycles of latency per step, 2 warps per
-// scheduler cannot hide it).  Here the two q rows of a warp run half a step apart:
-//     time 2t   : A.setup(t)   ||  B.dense(t-1) = rotate (p_{t-2}, q_b), fused with the NEXT dot (p_{t-1}', q_b')
-//     time 2t+1 : B.setup(t)   ||  A.dense(t)   = rotate (p_t, q_a),     fused with the NEXT dot (p_{t+1}, q_a')
-// so every latency chain sits in the same basic block as 128 independent DFMAs of the other chain.  Everything is
-// branch-free: a pair below the threshold gets the identity rotation (c = 1, s = 0: exact), which is why the sweep
-// loop falls back to the skipping lock-step visit once most pairs of a sweep no longer rotate.
-// No dot is ever stale: B touches p_{t-1} only after A.dense(t-1), and for NP >= 3 the tail of the previous slot's
-// q_b (rows p_{NP-2}, p_{NP-1} at times 0 and 2) is over before A's dots with those rows are formed (times >= 2NP-5).
-// ------------------------------------------------------------------------------------------------
-struct RotP {
-  double cs, sr, si;
-};
-
-// butterfly-reduce the lane partials of g = p . conj(q), then the rotation of tcb::make_rot (FP64 branch) for the rows
-// with squared norms (ai, aj); identity when the pair is inactive or below the threshold.  Norms updated in place.
-// Returns bit0 = rotated, bit1 = rotation not yet small.
-__device__ __forceinline__ int setup1(double gr, double gi, double &ai, double &aj, bool act, double dead, double tol2,
-                                      RotP &r) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    gr += __shfl_xor_sync(FULLM, gr, o);
-    gi += __shfl_xor_sync(FULLM, gi, o);
-  }
-  const double g2 = fma(gr, gr, gi * gi);
-  const double thr = ai * aj;
-  const bool rot = act && ai > dead && aj > dead && (g2 > tol2 * thr);
-  const bool big = rot && (g2 > tcj::SMALL_REL2 * thr);
-  const double dd = aj - ai;
-  const double rinv = rsqrt_nb(rot ? fma(dd, dd, 4.0 * g2) : 1.0);  // 1 / (2r)
-  const double c2 = fma(0.5 * fabs(dd), rinv, 0.5);
-  const double cinv = rsqrt_nb(c2);
-  const double ks = copysign(rinv * cinv, dd);
-  r.cs = rot ? c2 * cinv : 1.0;
-  r.sr = rot ? ks * gr : 0.0;
-  r.si = rot ? ks * gi : 0.0;
-  const double tg = rot ? g2 * ks * cinv : 0.0;
-  ai -= tg;
-  aj += tg;
-  return (int)rot | ((int)big << 1);
-}
-
-// rotate (u, v), then the lane partials of the next dot  w . conj(v')
-template <int NPL>
-__device__ __forceinline__ void dense(cplx (&u)[NPL], cplx (&v)[NPL], const RotP &r, const cplx (&w)[NPL], double &gr,
-                                      double &gi) {
-  double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
-#pragma unroll
-  for (int e = 0; e < NPL; ++e) {
-    cplx un, vn;
-    un.x = fma(r.cs, u[e].x, fma(-r.sr, v[e].x, r.si * v[e].y));
-    un.y = fma(r.cs, u[e].y, -fma(r.sr, v[e].y, r.si * v[e].x));
-    vn.x = fma(r.cs, v[e].x, fma(r.sr, u[e].x, r.si * u[e].y));
-    vn.y = fma(r.cs, v[e].y, fma(r.sr, u[e].y, -r.si * u[e].x));
-    u[e] = un;
-    v[e] = vn;
-    g0 = fma(w[e].x, vn.x, g0);
-    g1 = fma(w[e].y, vn.y, g1);
-    h0 = fma(w[e].y, vn.x, h0);
-    h1 = fma(-w[e].x, vn.y, h1);
-  }
-  gr = g0 + g1;
-  gi = h0 + h1;
-}
-
-// One slot of the pipelined visit.  HAS_A: this slot brings a new pair of q rows (q_a = row ja, q_b = row ja + 1);
-// HAS_B: the previous slot's q_b (row jbp) is still finishing.  First slot <true, false>, drain <false, true>.
-template <int NPL, bool FULL, int NP, bool HAS_A, bool HAS_B>
-__device__ __forceinline__ int slot_sp(cplx (&u)[PR][NPL], double (&pn)[PR], unsigned pvalid, cplx (&vA)[NPL],
-                                       cplx (&vB)[NPL], double &nB, bool &okB, double &gBr, double &gBi, RotP &rB,
-                                       cplx *Q, double *qn, int rowsQ, int N, uint32_t vaddr, int base, int s, int ja,
-                                       int jbp, int lane, double dead, double tol2 TCR_ARG) {
-  int fl = 0;  // bits 0..15: rotations, 16..31: rotations not yet small
-  RotP rA;
-  double nA = 0.0, gAr = 0.0, gAi = 0.0;
-  bool okA = false;
-  if (HAS_A) {
-    TCR_T(tw0);
-    if (s > 0) ver_wait(vaddr + 4 * ja, base + s);
-    TCR_T(tw1);
-    TCR_ACC(2, tw0, tw1);
-    okA = ja < rowsQ;
-    ld_row<NPL, FULL>(vA, Q + (size_t)(okA ? ja : 0) * N, N, lane);
-    nA = okA ? qn[ja] : 0.0;
-    dot_rows<NPL>(u[0], vA, gAr, gAi);
-  }
-  auto acc = [&](int f) { fl += (f & 1) + ((f & 2) << 15); };
-  // ---- time 0: A.setup(0) || B.dense(NP-1) of the previous slot
-  if (HAS_A) acc(setup1(gAr, gAi, pn[0], nA, okA && (pvalid & 1u), dead, tol2, rA));
-  if (HAS_B) dense<NPL>(u[NP - 2], vB, rB, u[NP - 1], gBr, gBi);
-  // ---- time 1: B.setup(NP) || A.dense(0)
-  if (HAS_B) acc(setup1(gBr, gBi, pn[NP - 1], nB, okB && ((pvalid >> (NP - 1)) & 1u), dead, tol2, rB));
-  if (HAS_A) dense<NPL>(u[0], vA, rA, u[1], gAr, gAi);
-  // ---- time 2: A.setup(1) || last rotation of the previous q_b, its store, the new q_b and its first dot
-  if (HAS_A) acc(setup1(gAr, gAi, pn[1], nA, okA && ((pvalid >> 1) & 1u), dead, tol2, rA));
-  if (HAS_B) {
-    rot_rows<NPL>(u[NP - 1], vB, rB.cs, rB.sr, rB.si);
-    if (okB) {
-      st_row<NPL, FULL>(vB, Q + (size_t)jbp * N, N, lane);
-      if (lane == 0) qn[jbp] = nB;
-    }
-    ver_release(vaddr + 4 * jbp, base + s, lane);  // use number s-1 of that row is over
-  }
-  if (HAS_A) {
-    const int jb = ja + 1;
-    TCR_T(tw2);
-    if (s > 0) ver_wait(vaddr + 4 * jb, base + s);
-    TCR_T(tw3);
-    TCR_ACC(2, tw2, tw3);
-    okB = jb < rowsQ;
-    ld_row<NPL, FULL>(vB, Q + (size_t)(okB ? jb : 0) * N, N, lane);
-    nB = okB ? qn[jb] : 0.0;
-    dot_rows<NPL>(u[0], vB, gBr, gBi);
-    // ---- times 2t+1, 2t+2
-#pragma unroll
-    for (int t = 1; t < NP; ++t) {
-      acc(setup1(gBr, gBi, pn[t - 1], nB, okB && ((pvalid >> (t - 1)) & 1u), dead, tol2, rB));  // B.setup(t)
-      if (t < NP - 1) {
-        dense<NPL>(u[t], vA, rA, u[t + 1], gAr, gAi);                                               // A.dense(t)
-        acc(setup1(gAr, gAi, pn[t + 1], nA, okA && ((pvalid >> (t + 1)) & 1u), dead, tol2, rA));  // A.setup(t+1)
-        dense<NPL>(u[t - 1], vB, rB, u[t], gBr, gBi);                                               // B.dense(t)
-      } else {
-        rot_rows<NPL>(u[t], vA, rA.cs, rA.sr, rA.si);  // last rotation of q_a; B.dense(NP-1) opens the next slot
-      }
-    }
-    if (okA) {
-      st_row<NPL, FULL>(vA, Q + (size_t)ja * N, N, lane);
-      if (lane == 0) qn[ja] = nA;
-    }
-    ver_release(vaddr + 4 * ja, base + s + 1, lane);
-  }
-  return fl;
-}
-
-template <int NPL, bool FULL, int NP, class Mid>
-__device__ __forceinline__ int visit_sp(cplx (&u)[PR][NPL], double (&pn)[PR], unsigned pvalid, cplx *Q, double *qn,
-                                        int rowsQ, int N, int *ver, int base, int warp, int lane, double dead,
-                                        double tol2, Mid &&mid TCR_ARG) {
-  static_assert(NP >= 3, "the pipelined visit needs three stationary rows per warp (stale-dot hazard otherwise)");
-  cplx vA[NPL], vB[NPL];
-  double nB = 0.0, gBr = 0.0, gBi = 0.0;
-  bool okB = false;
-  RotP rB;
-  rB.cs = 1.0;
-  rB.sr = rB.si = 0.0;
-  const uint32_t vaddr = smem_u32(ver);
-  int fl = slot_sp<NPL, FULL, NP, true, false>(u, pn, pvalid, vA, vB, nB, okB, gBr, gBi, rB, Q, qn, rowsQ, N, vaddr, base,
-                                               0, 2 * warp, 0, lane, dead, tol2 TCR_PASS);
-#pragma unroll 1
-  for (int s = 1; s < NW; ++s) {
-    if (s == NW / 2) mid();
-    const int ja = 2 * ((warp + s) & (NW - 1)), jbp = 2 * ((warp + s - 1) & (NW - 1)) + 1;
-    fl += slot_sp<NPL, FULL, NP, true, true>(u, pn, pvalid, vA, vB, nB, okB, gBr, gBi, rB, Q, qn, rowsQ, N, vaddr, base, s,
-                                             ja, jbp, lane, dead, tol2 TCR_PASS);
-  }
-  fl += slot_sp<NPL, FULL, NP, false, true>(u, pn, pvalid, vA, vB, nB, okB, gBr, gBi, rB, Q, qn, rowsQ, N, vaddr, base, NW,
-                                            0, 2 * ((warp + NW - 1) & (NW - 1)) + 1, lane, dead, tol2 TCR_PASS);
-  return fl;
 }
 
 // Internal pairs of a P block that sits in shared memory (H1 = rows 0..rows1-1 in the stage-0 area, H2 = rows2 rows
@@ -538,7 +372,7 @@ __device__ __forceinline__ int internal_phase(int n2, int row0, int rows1, int r
       pvalid |= (ok ? 1u : 0u) << k;
     }
     nrot += visit<NPL, FULL, 2>(u, pn, pvalid, H2, nP0 + QB, rows2, N, s_ver + QB, verBase1, warp, lane, dead, tol2,
-                                [] {} TCR_PASS) >> 16;
+                                [] {} TCR_PASS);
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const int r = 2 * warp + k;
@@ -551,15 +385,7 @@ __device__ __forceinline__ int internal_phase(int n2, int row0, int rows1, int r
   return nrot;
 }
 
-// Sweeps of one matrix.  SP = true: pipelined streaming visits, runs while at least half of the streaming pairs of a
-// sweep still rotate (identity rotations cost the pipelined visit as much as real ones), then hands the matrix over;
-// SP = false: skipping lock-step visits until convergence.  The two live in two kernels (launched back to back) so
-// that each streaming loop gets its own register allocation: side by side in one kernel they spill ~750 instructions
-// per slot, as __noinline__ functions ~200, alone 10-80.
-// `state` (one int per matrix, the knew slot finalize_kernel overwrites later): sweeps done | CONVERGED.
-constexpr int CONVERGED = 1 << 20;
-
-template <int NPL, bool FULL, bool SP>
+template <int NPL, bool FULL>
 __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int *s_rot, double *red) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cplx *const sQ = reinterpret_cast<cplx *>(smem_raw);  // stage k = sQ + k * QB * N; a P block fills both
@@ -575,33 +401,12 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
   const uint32_t row_bytes = (uint32_t)N * sizeof(cplx);
   uint32_t phP = 0, phQ0 = 0, phQ1 = 0;
   int verBase0 = 0, verBase1 = 0;
-  int *const state = d.knew + b.slot;
-  // streaming pairs per sweep (all pairs minus the P-block internal ones) for the pipelined / skipping switch
-  int stream_pairs = K * (K - 1) / 2;
-  for (int a = 0; a < nP; ++a) {
-    const int rp = min(PB, K - a * PB);
-    stream_pairs -= rp * (rp - 1) / 2;
-  }
-  // d.rot64 bit 2: always the skipping lock-step visit, bit 3: always the pipelined visit (A/B testing)
-  const int force = (d.rot64 >> 2) & 3;
   int sweep = 0;
-  bool converged = false;
-  if (SP) {
-    if (force == 1 || stream_pairs == 0) {
-      if (tid == 0) *state = 0;
-      return;
-    }
-  } else {
-    const int st = uni(*state);
-    if (st & CONVERGED) return;
-    sweep = st;
-  }
 #ifdef TCB_TIMING
   long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long tk0 = clock64();
 #endif
   double dead = 0.0;
-  bool first = true;
   for (; sweep < tcj::MAX_SWEEPS; ++sweep) {
     // all stores of the previous sweep have landed before rows are re-read
     if (tid == 0) bulk_wait_all();
@@ -613,16 +418,14 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
       s = tcj::warp_sum(s);
       if (lane == 0) s_nrm2[r] = s;
     }
-    if (tid == 0) s_rot[0] = s_rot[1] = 0;
+    if (tid == 0) *s_rot = 0;
     __syncthreads();
-    if (first) {
-      // |theta|_F^2 is invariant under the rotations: the hand-over kernel recomputes the same threshold
+    if (sweep == 0) {
       double p = 0.0;
       for (int r = tid; r < K; r += NT) p += s_nrm2[r];
       dead = tcj::DEAD_REL2 * block_sum(p, red);
-      first = false;
     }
-    int nrot = 0, nstream = 0;  // rotations not yet small (all phases); rotations of the streaming phase
+    int nrot = 0;  // rotations that were not yet small
     for (int a = 0; a < nP; ++a) {
       const int row0 = a * PB;
       const int rowsP = min(PB, K - row0);
@@ -695,15 +498,8 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
             bulk_load(sQ + (size_t)(buf ^ 1) * QB * N, X + (size_t)(rq0 + QB) * N, rq * row_bytes, &barQ[buf ^ 1]);
           }
         };
-        int fl;
-        if (SP)
-          fl = visit_sp<NPL, FULL, PR>(u, pn, pvalid, Q, s_nrm2 + rq0, rowsQ, N, s_ver + buf * QB,
-                                       buf ? verBase1 : verBase0, warp, lane, dead, tol2, refill TCR_PASS);
-        else
-          fl = visit<NPL, FULL, PR>(u, pn, pvalid, Q, s_nrm2 + rq0, rowsQ, N, s_ver + buf * QB,
-                                    buf ? verBase1 : verBase0, warp, lane, dead, tol2, refill TCR_PASS);
-        nrot += fl >> 16;
-        nstream += fl & 0xffff;
+        nrot += visit<NPL, FULL, PR>(u, pn, pvalid, Q, s_nrm2 + rq0, rowsQ, N, s_ver + buf * QB,
+                                     buf ? verBase1 : verBase0, warp, lane, dead, tol2, refill TCR_PASS);
         if (buf)
           verBase1 += NW;
         else
@@ -732,19 +528,11 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
       asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy stores before later bulk (async-proxy) loads
       __syncthreads();
     }
-    if (lane == 0 && nrot) atomicAdd(&s_rot[0], nrot);
-    if (lane == 0 && nstream) atomicAdd(&s_rot[1], nstream);
+    if (lane == 0 && nrot) atomicAdd(s_rot, nrot);
     __syncthreads();
-    const int tot = uni(s_rot[0]), tot_stream = uni(s_rot[1]);
+    const int tot = uni(*s_rot);
     __syncthreads();
-    if (tot == 0) {
-      converged = true;
-      break;
-    }
-    if (SP && force != 2 && 2 * tot_stream <= stream_pairs) {
-      ++sweep;
-      break;  // hand over to the skipping kernel
-    }
+    if (tot == 0) break;
   }
 #ifdef TCB_TIMING
   if (K == 256 && N == 256 && warp == 3 && lane == 0) {
@@ -752,13 +540,8 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
     for (int k = 0; k < 8; ++k) atomicAdd(&tcb::g_tcb_timing[k], (unsigned long long)tacc[k]);
   }
 #endif
-  if (tid == 0) bulk_wait_all();
-  if (SP && !converged && sweep < tcj::MAX_SWEEPS) {
-    if (tid == 0) *state = sweep;
-    return;
-  }
   if (tid == 0) {
-    *state = CONVERGED;
+    bulk_wait_all();
     if (sweep >= tcj::MAX_SWEEPS) atomicAdd(&d.flags[1], 1);
     atomicMax(&d.flags[2], sweep + 1);
     if (K >= 128) {  // sweep statistics of the large matrices (diagnostics)
@@ -777,15 +560,6 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
   }
 }
 
-// Largest matrices first: CTA x of chain y works on the bonds from the centre of the chain outwards, so the
-// full-size updates start in the first wave and the small edge bonds fill the tail.
-__device__ __forceinline__ int centre_out(int x, int nb) {
-  const int c = nb / 2;
-  const int k = (x + 1) / 2;
-  return (x & 1) ? c - k : c + k;  // x = 0 -> c, 1 -> c-1, 2 -> c+1, ...: a bijection of [0, nb) for odd and even nb
-}
-
-template <bool SP>
 __global__ void __launch_bounds__(NT, 1) jacobi_rb_kernel(TcDev d, LayerArgs a) {
   Bond b;
   // blockIdx.x = chain, blockIdx.y = rank of the bond in centre-out order
@@ -795,7 +569,7 @@ __global__ void __launch_bounds__(NT, 1) jacobi_rb_kernel(TcDev d, LayerArgs a) 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)2 * QB * d.n2 * sizeof(cplx) + d.n2 * sizeof(double));
   __shared__ double red[32];
-  __shared__ int s_rot[2];
+  __shared__ int s_rot;
   if (threadIdx.x == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -806,14 +580,14 @@ __global__ void __launch_bounds__(NT, 1) jacobi_rb_kernel(TcDev d, LayerArgs a) 
   __syncthreads();
   const int npl = (N + 31) / 32;
   if (N == 256)
-    sweeps<8, true, SP>(d, b, X, K, N, s_rot, red);
+    sweeps<8, true>(d, b, X, K, N, &s_rot, red);
   else if (npl <= 1)
-    sweeps<1, false, SP>(d, b, X, K, N, s_rot, red);
+    sweeps<1, false>(d, b, X, K, N, &s_rot, red);
   else if (npl <= 2)
-    sweeps<2, false, SP>(d, b, X, K, N, s_rot, red);
+    sweeps<2, false>(d, b, X, K, N, &s_rot, red);
   else if (npl <= 4)
-    sweeps<4, false, SP>(d, b, X, K, N, s_rot, red);
+    sweeps<4, false>(d, b, X, K, N, &s_rot, red);
   else
-    sweeps<8, false, SP>(d, b, X, K, N, s_rot, red);
+    sweeps<8, false>(d, b, X, K, N, &s_rot, red);
 }
 }  // namespace tcr
