@@ -84,6 +84,7 @@ struct LayerArgs {
   int kick_mode;   // bit0: kick both sites of every bond; bit1: kick right site of bond i == L-2
   const cplx *gate_override;  // != nullptr: this 4x4 gate for every bond instead of d.gates
   int diag;                   // the gates of this launch are diagonal: phase fused into the GEMM epilogue
+  int slot0;                  // first workspace chain slot of this launch (chain groups own disjoint slot ranges)
 };
 
 struct Bond {
@@ -104,7 +105,7 @@ __device__ __forceinline__ bool get_bond(const TcDev &d, const LayerArgs &a, int
   b.chiR = c[b.i + 2];
   b.M = 2 * b.chiL;
   b.N = 2 * b.chiR;
-  b.slot = (size_t)ry * d.nbmax + jb;
+  b.slot = (size_t)(a.slot0 + ry) * d.nbmax + jb;
   return true;
 }
 

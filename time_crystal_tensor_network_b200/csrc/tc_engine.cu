@@ -67,6 +67,12 @@ struct tc_ctx {
   bool rb_attr_set = false;
   int jacobi_kind = 1;  // TC_JACOBI = blocked (1, default: 16-warp kernel) | rb (2: register-blocked, experimental) | simple (0)
   bool force_simple_jacobi = false;  // TC_JACOBI=simple: the warp-per-pair kernel for every size (A/B testing)
+  // chain groups: the chains never interact, so G groups run their periods on G streams and the tail of one group's
+  // layer (fewer CTAs than SMs left) overlaps the next kernels of the others.  TC_GROUPS, default 4.
+  int ngroups = 1;
+  std::vector<cudaStream_t> gstreams;
+  std::vector<cudaEvent_t> gjoin;
+  cudaEvent_t gfork = nullptr;
   // record buffers for tc_floquet_run_host
   void *rec = nullptr;
   size_t rec_bytes = 0;
@@ -337,31 +343,32 @@ static bool gates_all_diagonal(const double *g, size_t n_gates) {
 }
 
 // one group of two-site updates: bonds first_site + 2 jb, jb < nb, on chains [r_lo, r_hi)
+// `st`, `ws_lo`, `ws_n`: the stream to launch on and the range of workspace chain slots this call may use
 static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int kick_mode, const cplx *gate_override,
-                     int diag) {
+                     int diag, cudaStream_t st, int ws_lo, int ws_n) {
   if (nb <= 0 || r_hi <= r_lo) return 0;
   const TcDev &d = c->d;
   const int tiles1 = (d.n2 + tcg::BM - 1) / tcg::BM;
   const int tiles = tiles1 * tiles1;
-  for (int r0 = r_lo; r0 < r_hi; r0 += d.ws_chains) {
-    const int nr = (r_hi - r0) < d.ws_chains ? (r_hi - r0) : d.ws_chains;
-    LayerArgs a{first_site, 2, nb, r0, nr, kick_mode, gate_override, diag};
+  for (int r0 = r_lo; r0 < r_hi; r0 += ws_n) {
+    const int nr = (r_hi - r0) < ws_n ? (r_hi - r0) : ws_n;
+    LayerArgs a{first_site, 2, nb, r0, nr, kick_mode, gate_override, diag, ws_lo};
     {
       ProfScope ps(c, TC_PROF_THETA);
-      tcg::gemm_kernel<ThetaPolicy><<<dim3(tiles, nb, nr), tcg::NT, 0, c->stream>>>(d, a);
+      tcg::gemm_kernel<ThetaPolicy><<<dim3(tiles, nb, nr), tcg::NT, 0, st>>>(d, a);
       LAUNCHED();
       if (!diag) {
         const int gx = (d.chi_cap * d.chi_cap + 255) / 256;
-        gate_mix_kernel<<<dim3(gx, nb, nr), 256, 0, c->stream>>>(d, a);
+        gate_mix_kernel<<<dim3(gx, nb, nr), 256, 0, st>>>(d, a);
         LAUNCHED();
       }
     }
     {
       ProfScope ps(c, TC_PROF_QR);
       if (d.n2 <= tcj::QMAXM && !c->force_simple_jacobi)
-        tcj::qr_blocked_kernel<<<dim3(nr, nb), tcj::QNT, 0, c->stream>>>(d, a);
+        tcj::qr_blocked_kernel<<<dim3(nr, nb), tcj::QNT, 0, st>>>(d, a);
       else
-        tcj::qr_kernel<<<dim3(nb, nr), tcj::NT, (d.n2 + 64) * sizeof(cplx), c->stream>>>(d, a);
+        tcj::qr_kernel<<<dim3(nb, nr), tcj::NT, (d.n2 + 64) * sizeof(cplx), st>>>(d, a);
       LAUNCHED();
     }
     {
@@ -372,38 +379,41 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
           CK(cudaFuncSetAttribute(tcr::jacobi_rb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           c->rb_attr_set = true;
         }
-        tcr::jacobi_rb_kernel<<<dim3(nr, nb), tcr::NT, smem, c->stream>>>(d, a);
+        tcr::jacobi_rb_kernel<<<dim3(nr, nb), tcr::NT, smem, st>>>(d, a);
       } else if (d.n2 <= tcb::MAX_N && !c->force_simple_jacobi) {
         const size_t smem = (size_t)3 * tcb::BR * d.n2 * sizeof(cplx) + d.n2 * sizeof(double) + 64 + 2 * tcb::BR * sizeof(int);
         if (!c->blocked_attr_set) {
           CK(cudaFuncSetAttribute(tcb::jacobi_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           c->blocked_attr_set = true;
         }
-        tcb::jacobi_blocked_kernel<<<dim3(nr, nb), tcb::NT, smem, c->stream>>>(d, a);
+        tcb::jacobi_blocked_kernel<<<dim3(nr, nb), tcb::NT, smem, st>>>(d, a);
       } else {
-        tcj::jacobi_rows_kernel<<<dim3(nb, nr), tcj::NT, d.n2 * sizeof(double), c->stream>>>(d, a);
+        tcj::jacobi_rows_kernel<<<dim3(nb, nr), tcj::NT, d.n2 * sizeof(double), st>>>(d, a);
       }
       LAUNCHED();
     }
     {
       ProfScope ps(c, TC_PROF_FINALIZE);
-      tcj::finalize_kernel<<<dim3(nb, nr), tcj::NT, d.n2 * sizeof(double), c->stream>>>(d, a);
+      tcj::finalize_kernel<<<dim3(nb, nr), tcj::NT, d.n2 * sizeof(double), st>>>(d, a);
       LAUNCHED();
     }
     {
       ProfScope ps(c, TC_PROF_BLEFT);
-      tcg::gemm_kernel<BLPolicy><<<dim3(tiles, nb, nr), tcg::NT, 0, c->stream>>>(d, a);
+      tcg::gemm_kernel<BLPolicy><<<dim3(tiles, nb, nr), tcg::NT, 0, st>>>(d, a);
       LAUNCHED();
     }
   }
   return 0;
 }
 
-static int run_layer(tc_ctx *c, int parity, int kick_mode) {
+static int run_layer_on(tc_ctx *c, int parity, int kick_mode, int r_lo, int r_hi, cudaStream_t st, int ws_lo, int ws_n) {
   const int L = c->d.L;
   if (L < 2) return 0;
   const int nb = (L - 1 - parity + 1) / 2;  // bonds parity, parity+2, ... <= L-2
-  return run_bonds(c, parity, nb, 0, c->d.R, kick_mode, nullptr, c->d.gates_diag);
+  return run_bonds(c, parity, nb, r_lo, r_hi, kick_mode, nullptr, c->d.gates_diag, st, ws_lo, ws_n);
+}
+static int run_layer(tc_ctx *c, int parity, int kick_mode) {
+  return run_layer_on(c, parity, kick_mode, 0, c->d.R, c->stream, 0, c->d.ws_chains);
 }
 
 static int run_kick_all(tc_ctx *c) {
@@ -413,15 +423,56 @@ static int run_kick_all(tc_ctx *c) {
   return 0;
 }
 
-// even, odd, kick (fused into the loads of the second Ising layer), even, odd
-static int run_period(tc_ctx *c) {
+// even, odd, kick (fused into the loads of the second Ising layer), even, odd -- for the chains [r_lo, r_hi)
+static int run_period_on(tc_ctx *c, int r_lo, int r_hi, cudaStream_t st, int ws_lo, int ws_n) {
   const int L = c->d.L;
-  if (L < 2) return run_kick_all(c);
-  if (run_layer(c, 0, 0)) return 1;
-  if (run_layer(c, 1, 0)) return 1;
-  if (run_layer(c, 0, 1)) return 1;  // the even bonds cover sites 0 .. 2*floor(L/2)-1
+  if (run_layer_on(c, 0, 0, r_lo, r_hi, st, ws_lo, ws_n)) return 1;
+  if (run_layer_on(c, 1, 0, r_lo, r_hi, st, ws_lo, ws_n)) return 1;
+  if (run_layer_on(c, 0, 1, r_lo, r_hi, st, ws_lo, ws_n)) return 1;  // the even bonds cover sites 0 .. 2*floor(L/2)-1
   if (L == 2) return 0;
-  return run_layer(c, 1, (L & 1) ? 2 : 0);  // odd L: site L-1 is the right site of the last odd bond
+  // odd L: site L-1 is the right site of the last odd bond
+  return run_layer_on(c, 1, (L & 1) ? 2 : 0, r_lo, r_hi, st, ws_lo, ws_n);
+}
+
+// n Floquet periods of every chain.  With G > 1 chain groups each group runs all its n periods on its own stream
+// (fork after what is already queued on the context's stream, join before what comes next); per-kernel profiling
+// needs the launches in one stream and runs the groups one after the other.
+static int run_periods(tc_ctx *c, int n) {
+  const TcDev &d = c->d;
+  if (n <= 0) return 0;
+  if (d.L < 2) {
+    for (int t = 0; t < n; ++t)
+      if (run_kick_all(c)) return 1;
+    return 0;
+  }
+  int G = c->ngroups;
+  if (G > d.R) G = d.R;
+  if (G > d.ws_chains) G = d.ws_chains;
+  if (c->profile || G <= 1) {
+    for (int t = 0; t < n; ++t)
+      if (run_period_on(c, 0, d.R, c->stream, 0, d.ws_chains)) return 1;
+    return 0;
+  }
+  while ((int)c->gstreams.size() < G) {
+    cudaStream_t s;
+    CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    c->gstreams.push_back(s);
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    c->gjoin.push_back(e);
+  }
+  if (!c->gfork) CK(cudaEventCreateWithFlags(&c->gfork, cudaEventDisableTiming));
+  CK(cudaEventRecord(c->gfork, c->stream));
+  const int wpg = d.ws_chains / G;
+  for (int g = 0; g < G; ++g) {
+    const int r_lo = (int)((long long)d.R * g / G), r_hi = (int)((long long)d.R * (g + 1) / G);
+    CK(cudaStreamWaitEvent(c->gstreams[g], c->gfork, 0));
+    for (int t = 0; t < n; ++t)
+      if (run_period_on(c, r_lo, r_hi, c->gstreams[g], g * wpg, wpg)) return 1;
+    CK(cudaEventRecord(c->gjoin[g], c->gstreams[g]));
+  }
+  for (int g = 0; g < G; ++g) CK(cudaStreamWaitEvent(c->stream, c->gjoin[g], 0));
+  return 0;
 }
 
 static int measure_into(tc_ctx *c, double *rdm, double *Z, double *ent, double *ov, int32_t *chi) {
@@ -487,6 +538,8 @@ int tc_ctx_create(int device, int L, int chi_cap, int R, void *arena, size_t are
     c->own_arena = true;
   }
   c->arena_bytes = lo.total;
+  c->ngroups = 4;
+  if (const char *e = getenv("TC_GROUPS")) c->ngroups = atoi(e) > 0 ? atoi(e) : 1;
   if (const char *e = getenv("TC_JACOBI")) {
     c->force_simple_jacobi = strcmp(e, "simple") == 0;
     c->jacobi_kind = strcmp(e, "simple") == 0 ? 0 : (strcmp(e, "rb") == 0 ? 2 : 1);
@@ -567,6 +620,9 @@ int tc_ctx_destroy(tc_ctx *c) {
   for (auto e : c->free_events) cudaEventDestroy(e);
   if (c->rec) cudaFree(c->rec);
   if (c->own_arena) cudaFree(c->arena);
+  for (cudaStream_t gs : c->gstreams) cudaStreamDestroy(gs);
+  for (cudaEvent_t e : c->gjoin) cudaEventDestroy(e);
+  if (c->gfork) cudaEventDestroy(c->gfork);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -788,9 +844,7 @@ int tc_apply_kick(tc_ctx *c) {
 int tc_floquet_step(tc_ctx *c, int n_steps) {
   CTX(c);
   if (!c->have_model) return fail("tc_floquet_step: no model set");
-  for (int t = 0; t < n_steps; ++t)
-    if (run_period(c)) return 1;
-  return 0;
+  return run_periods(c, n_steps);
 }
 
 int tc_apply_two_site(tc_ctx *c, int r, int site, const double *gate_host) {
@@ -801,7 +855,7 @@ int tc_apply_two_site(tc_ctx *c, int r, int site, const double *gate_host) {
   CK(cudaMemcpyAsync(c->op_scratch, gate_host, 16 * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   const int diag = gates_all_diagonal(gate_host, 1) ? 1 : 0;
-  return run_bonds(c, site, 1, r, r + 1, 0, c->op_scratch, diag);
+  return run_bonds(c, site, 1, r, r + 1, 0, c->op_scratch, diag, c->stream, 0, c->d.ws_chains);
 }
 
 int tc_apply_one_site(tc_ctx *c, int r, int site, const double *op_host) {
@@ -909,12 +963,16 @@ int tc_floquet_run_dev(tc_ctx *c, int n_steps, int measure_every, int rec0, int 
     if (rec(k)) return 1;
     ++k;
   }
-  for (int t = 0; t < n_steps; ++t) {
-    if (run_period(c)) return 1;
-    if (t % measure_every == 0) {
-      if (rec(k)) return 1;
-      ++k;
-    }
+  // periods t = 0 .. n_steps-1, a record after every period with t % measure_every == 0; the periods between two
+  // records go to run_periods in one call (the chain groups only join where a record needs every chain)
+  int t = 0;
+  while (t < n_steps) {
+    const int tn = (t + measure_every - 1) / measure_every * measure_every;  // next recorded period
+    if (tn >= n_steps) return run_periods(c, n_steps - t);
+    if (run_periods(c, tn - t + 1)) return 1;
+    if (rec(k)) return 1;
+    ++k;
+    t = tn + 1;
   }
   return 0;
 }
