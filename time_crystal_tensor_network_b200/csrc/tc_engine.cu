@@ -65,11 +65,14 @@ struct tc_ctx {
   bool have_model = false;
   bool blocked_attr_set = false;
   bool rb_attr_set = false;
+  bool qrw_attr_set = false;
   int jacobi_kind = 1;  // TC_JACOBI = blocked (1, default: 16-warp kernel) | rb (2: register-blocked, experimental) | simple (0)
   bool force_simple_jacobi = false;  // TC_JACOBI=simple: the warp-per-pair kernel for every size (A/B testing)
   // chain groups: the chains never interact, so G groups run their periods on G streams and the tail of one group's
   // layer (fewer CTAs than SMs left) overlaps the next kernels of the others.  TC_GROUPS, default 4.
   int ngroups = 1;
+  int sm_count = 148;
+  int wide_cluster = 0;  // TC_WIDE_CLUSTER: CTAs per matrix of the wide (chi_cap > 128) Jacobi kernel, 0 = automatic
   std::vector<cudaStream_t> gstreams;
   std::vector<cudaEvent_t> gjoin;
   cudaEvent_t gfork = nullptr;
@@ -365,10 +368,18 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
     }
     {
       ProfScope ps(c, TC_PROF_QR);
-      if (d.n2 <= tcj::QMAXM && !c->force_simple_jacobi)
-        tcj::qr_blocked_kernel<<<dim3(nr, nb), tcj::QNT, 0, st>>>(d, a);
-      else
+      if (d.n2 <= tcj::QMAXM && !c->force_simple_jacobi) {
+        tcj::qr_blocked_kernel<tcj::QNT><<<dim3(nr, nb), tcj::QNT, tcj::QNT * tcj::QB * sizeof(cplx), st>>>(d, a);
+      } else if (d.n2 <= tcj::QMAXMW && !c->force_simple_jacobi) {
+        const int smem = tcj::QNTW * tcj::QB * (int)sizeof(cplx);  // 64 KB V panel
+        if (!c->qrw_attr_set) {
+          CK(cudaFuncSetAttribute(tcj::qr_blocked_kernel<tcj::QNTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+          c->qrw_attr_set = true;
+        }
+        tcj::qr_blocked_kernel<tcj::QNTW><<<dim3(nr, nb), tcj::QNTW, smem, st>>>(d, a);
+      } else {
         tcj::qr_kernel<<<dim3(nb, nr), tcj::NT, (d.n2 + 64) * sizeof(cplx), st>>>(d, a);
+      }
       LAUNCHED();
     }
     {
@@ -388,7 +399,27 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
         }
         tcb::jacobi_blocked_kernel<<<dim3(nr, nb), tcb::NT, smem, st>>>(d, a);
       } else {
-        tcj::jacobi_rows_kernel<<<dim3(nb, nr), tcj::NT, d.n2 * sizeof(double), st>>>(d, a);
+        // wide matrices: a cluster of CS CTAs per matrix when the launch has too few matrices to fill the GPU
+        int CS = 1;
+        while (CS < 8 && (long long)nb * nr * CS * 2 <= c->sm_count) CS *= 2;  // 190 registers: one CTA per SM
+        if (c->wide_cluster > 0) CS = c->wide_cluster;
+        if (CS > 1 && !c->force_simple_jacobi && d.n2 <= 32 * tcj::WNPL) {
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3(nb * CS, nr);
+          cfg.blockDim = dim3(tcj::NT);
+          cfg.dynamicSmemBytes = 0;
+          cfg.stream = st;
+          cudaLaunchAttribute attr[1];
+          attr[0].id = cudaLaunchAttributeClusterDimension;
+          attr[0].val.clusterDim.x = CS;
+          attr[0].val.clusterDim.y = 1;
+          attr[0].val.clusterDim.z = 1;
+          cfg.attrs = attr;
+          cfg.numAttrs = 1;
+          CK(cudaLaunchKernelEx(&cfg, tcj::jacobi_rows_cluster_kernel, d, a, CS));
+        } else {
+          tcj::jacobi_rows_kernel<<<dim3(nb, nr), tcj::NT, d.n2 * sizeof(double), st>>>(d, a);
+        }
       }
       LAUNCHED();
     }
@@ -539,6 +570,8 @@ int tc_ctx_create(int device, int L, int chi_cap, int R, void *arena, size_t are
   }
   c->arena_bytes = lo.total;
   c->ngroups = 4;
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
+  if (const char *e = getenv("TC_WIDE_CLUSTER")) c->wide_cluster = atoi(e);
   if (const char *e = getenv("TC_GROUPS")) c->ngroups = atoi(e) > 0 ? atoi(e) : 1;
   if (const char *e = getenv("TC_JACOBI")) {
     c->force_simple_jacobi = strcmp(e, "simple") == 0;

@@ -148,10 +148,11 @@ __global__ void __launch_bounds__(NT) qr_kernel(TcDev d, LayerArgs a) {
 //             two passes over the trailing matrix per PANEL instead of per column.
 // static smem: V 32 KB + reduction scratch
 // ------------------------------------------------------------------------------------------------
-constexpr int QB = 8, QNT = 256, QMAXM = 256;
+constexpr int QB = 8, QNT = 256, QMAXM = 256;  // fast-path instance: M <= 256 rows, 256 threads
+constexpr int QNTW = 512, QMAXMW = 512;         // wide instance (chi_cap <= 256): M <= 512 rows, 512 threads
 
-// block-wide sums of NV doubles per thread; result in out[0..NV) (all threads), scratch [QNT/32][NV]
-template <int NV>
+// block-wide sums of NV doubles per thread; result in out[0..NV) (all threads), scratch [QT/32][NV]
+template <int NV, int QT>
 __device__ __forceinline__ void block_sum_vec(double (&v)[NV], double *scratch, int nv_used) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -169,20 +170,23 @@ __device__ __forceinline__ void block_sum_vec(double (&v)[NV], double *scratch, 
     if (k < nv_used) {
       double t = 0.0;
 #pragma unroll
-      for (int w = 0; w < QNT / 32; ++w) t += scratch[w * NV + k];
+      for (int w = 0; w < QT / 32; ++w) t += scratch[w * NV + k];
       v[k] = t;
     }
 }
 
-__global__ void __launch_bounds__(QNT) qr_blocked_kernel(TcDev d, LayerArgs a) {
+// QT threads = max rows; dynamic smem: V panel, QT * QB cplx
+template <int QT>
+__global__ void __launch_bounds__(QT) qr_blocked_kernel(TcDev d, LayerArgs a) {
   Bond b;
   // blockIdx.x = chain, blockIdx.y = rank of the bond in centre-out order (largest matrices first)
   if (!get_bond(d, a, centre_out(blockIdx.y, a.nb), blockIdx.x, b)) return;
   const int M = b.M, N = b.N;
   cplx *X = d.Xw + b.slot * d.slot_stride;
-  __shared__ __align__(16) cplx V[QMAXM * QB];
+  extern __shared__ __align__(16) unsigned char qr_smem_raw[];
+  cplx *const V = reinterpret_cast<cplx *>(qr_smem_raw);  // [QT][QB]
   __shared__ __align__(16) cplx Tm[QB * QB];
-  __shared__ double scratch[(QNT / 32) * 2 * QB];
+  __shared__ double scratch[(QT / 32) * 2 * QB];
   __shared__ cplx s_alpha;
   const int tid = threadIdx.x;
   const int steps = (M - 1) < N ? (M - 1) : N;  // columns that have something to annihilate
@@ -203,7 +207,7 @@ __global__ void __launch_bounds__(QNT) qr_blocked_kernel(TcDev d, LayerArgs a) {
         double red[2 * QB];
         red[0] = (have && tid > j) ? cabs2(p[j]) : 0.0;
         if (tid == j) s_alpha = p[j];
-        block_sum_vec<2 * QB>(red, scratch, 1);
+        block_sum_vec<2 * QB, QT>(red, scratch, 1);
         double beta;
         cplx sc;
         larfg(s_alpha, red[0], beta, tau[j], sc);
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(QNT) qr_blocked_kernel(TcDev d, LayerArgs a) {
             red[2 * c] = t.x;
             red[2 * c + 1] = t.y;
           }
-          block_sum_vec<2 * QB>(red, scratch, 2 * QB);
+          block_sum_vec<2 * QB, QT>(red, scratch, 2 * QB);
           const cplx tc = cconj(tau[j]);
 #pragma unroll
           for (int c = 0; c < QB; ++c)
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(QNT) qr_blocked_kernel(TcDev d, LayerArgs a) {
     {
       const int warp = tid >> 5, lane = tid & 31;
       __shared__ cplx G[QB * QB];
-      for (int pr = warp; pr < QB * QB; pr += QNT / 32) {
+      for (int pr = warp; pr < QB * QB; pr += QT / 32) {
         const int i = pr / QB, j = pr % QB;
         if (i < j) {
           cplx acc = cmake(0.0, 0.0);
@@ -406,6 +410,137 @@ __global__ void __launch_bounds__(NT) jacobi_rows_kernel(TcDev d, LayerArgs a) {
     for (int c = lane; c < N; c += 32) s += cabs2(row[c]);
     s = warp_sum(s);
     if (lane == 0) w[r] = sqrt(s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// v1c: the warp-per-pair kernel on a thread-block CLUSTER (matrices wider than the register-resident fast path,
+// chi_cap > 128, where a context holds few chains: BASELINE config 4 is ONE chain of 63 bonds, i.e. ~31 matrices of
+// 512 x 512 per layer -- one CTA per matrix would leave 4/5 of the SMs idle).  CS CTAs share a matrix: the M/2
+// disjoint pairs of a tournament round are dealt to the CS * 8 warps of the cluster, rows and row norms live in
+// global memory / L2 (ld.cg / st.cg: L1 is not coherent between the SMs of a cluster), one cluster barrier
+// (release / acquire, ~0.2 us) per round.  Scratch: the slot's `ww` row (squared norms, overwritten by the singular
+// values at the end) and its `knew` entry (rotation counter; finalize_kernel overwrites it).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+constexpr int WNPL = 16;  // complex elements per lane and row in the cluster kernel: matrices up to 512 columns
+
+__global__ void __launch_bounds__(NT) jacobi_rows_cluster_kernel(TcDev d, LayerArgs a, int CS) {
+  Bond b;
+  // every CTA of a cluster sees the same bond, so the cluster leaves or stays as a whole
+  if (!get_bond(d, a, centre_out(blockIdx.x / CS, a.nb), blockIdx.y, b)) return;
+  const int N = b.N, M = b.M < b.N ? b.M : b.N;  // rows of the triangular factor
+  cplx *X = d.Xw + b.slot * d.slot_stride;
+  double *nrm2 = d.ww + b.slot * d.n2;
+  int *cnt = d.knew + b.slot;
+  __shared__ double red[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = NT / 32;
+  const int rank = (int)cluster_rank();
+  const int gw = rank * NW + warp, nw = CS * NW;  // this warp among the warps of the cluster
+  const double tol = 2.0 * sqrt((double)N) * 2.220446049250313e-16;
+  const double tol2 = tol * tol;
+  double dead = 0.0;
+  int sweep = 0;
+  for (; sweep < MAX_SWEEPS; ++sweep) {
+    for (int r = gw; r < M; r += nw) {
+      const double2 *row = reinterpret_cast<const double2 *>(X + (size_t)r * N);
+      double s = 0.0;
+      for (int c = lane; c < N; c += 32) s += cabs2(__ldcg(row + c));
+      s = warp_sum(s);
+      if (lane == 0) __stcg(nrm2 + r, s);
+    }
+    if (gw == 0 && lane == 0) __stcg(cnt, 0);
+    cluster_sync_all();
+    if (sweep == 0) {
+      double p = 0.0;
+      for (int r = tid; r < M; r += NT) p += __ldcg(nrm2 + r);
+      dead = DEAD_REL2 * block_sum(p, red);
+    }
+    int nrot = 0;
+    for (int r = 0; r < M - 1; ++r) {
+      for (int k = gw; k < M / 2; k += nw) {
+        int i, j;
+        rr_pair(M, r, k, i, j);
+        const double ai = __ldcg(nrm2 + i), aj = __ldcg(nrm2 + j);
+        if (ai <= dead || aj <= dead) continue;
+        double2 *xi = reinterpret_cast<double2 *>(X + (size_t)i * N), *xj = reinterpret_cast<double2 *>(X + (size_t)j * N);
+        // both rows into registers with every load in flight at once (N <= 32 WNPL = 512 columns: 16 complex per lane
+        // and row); they stay there between the dot product and the rotation, so a pair costs one read and one
+        // write of its rows in L2 instead of two reads and a write
+        cplx u[WNPL], v[WNPL];
+#pragma unroll
+        for (int e = 0; e < WNPL; ++e) {
+          const int c = lane + 32 * e;
+          u[e] = c < N ? __ldcg(xi + c) : cmake(0.0, 0.0);
+          v[e] = c < N ? __ldcg(xj + c) : cmake(0.0, 0.0);
+        }
+        double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;  // g = sum x_i conj(x_j)
+#pragma unroll
+        for (int e = 0; e < WNPL; ++e) {
+          g0 = fma(u[e].x, v[e].x, g0);
+          g1 = fma(u[e].y, v[e].y, g1);
+          h0 = fma(u[e].y, v[e].x, h0);
+          h1 = fma(-u[e].x, v[e].y, h1);
+        }
+        double gr = warp_sum(g0 + g1);
+        double gi = warp_sum(h0 + h1);
+        const double g2 = gr * gr + gi * gi;
+        if (!(g2 > tol2 * ai * aj)) continue;
+        nrot += g2 > SMALL_REL2 * ai * aj;
+        const double ga = sqrt(g2);
+        const double zeta = (aj - ai) / (2.0 * ga);
+        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double cs = 1.0 / sqrt(1.0 + t * t);
+        const double sn = cs * t;
+        const double er = gr / ga, ei = gi / ga;  // e = g / |g|
+        const double sr = sn * er, si = sn * ei;  // s e
+        // x_i' = c x_i - (s e) x_j ;  x_j' = conj(s e) x_i + c x_j
+#pragma unroll
+        for (int e = 0; e < WNPL; ++e) {
+          const int c = lane + 32 * e;
+          cplx un, vn;
+          un.x = cs * u[e].x - (sr * v[e].x - si * v[e].y);
+          un.y = cs * u[e].y - (sr * v[e].y + si * v[e].x);
+          vn.x = cs * v[e].x + (sr * u[e].x + si * u[e].y);
+          vn.y = cs * v[e].y + (sr * u[e].y - si * u[e].x);
+          if (c < N) {
+            __stcg(xi + c, un);
+            __stcg(xj + c, vn);
+          }
+        }
+        if (lane == 0) {
+          __stcg(nrm2 + i, ai - t * ga);
+          __stcg(nrm2 + j, aj + t * ga);
+        }
+      }
+      cluster_sync_all();
+    }
+    if (lane == 0 && nrot) atomicAdd(cnt, nrot);
+    cluster_sync_all();
+    const int tot = __ldcg(cnt);
+    cluster_sync_all();  // everybody has read the counter before the next sweep clears it
+    if (tot == 0) break;
+  }
+  if (gw == 0 && lane == 0) {
+    if (sweep >= MAX_SWEEPS) atomicAdd(&d.flags[1], 1);
+    atomicMax(&d.flags[2], sweep + 1);
+  }
+  // singular values = final row norms (into the same ww row the squared norms lived in)
+  for (int r = gw; r < M; r += nw) {
+    const double2 *row = reinterpret_cast<const double2 *>(X + (size_t)r * N);
+    double s = 0.0;
+    for (int c = lane; c < N; c += 32) s += cabs2(__ldcg(row + c));
+    s = warp_sum(s);
+    if (lane == 0) nrm2[r] = sqrt(s);
   }
 }
 
