@@ -32,14 +32,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   uint32_t ok = 0;
   const uint32_t addr = smem_u32(bar);
   unsigned long long spins = 0;
-  while (!ok) {
+  do {  // exit on a warp vote: a uniform branch for the compiler (see the note on REDUX in the kernel)
     if (++spins > (1ull << 26)) __trap();  // a lost bulk copy must fail loudly, never hang the GPU
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(addr), "r"(parity)
         : "memory");
-  }
+  } while (__any_sync(0xffffffffu, ok == 0));
 }
 __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -71,6 +71,20 @@ struct Rot {
   double cs, sr, si, ni, nj;  // cos, s*e (complex), new squared norms
 };
 
+// 1/sqrt(x) for normal positive x without the special-case branch of rsqrt(double): hardware seed (MUFU.RSQ64H,
+// ~2^-22) and two Newton steps (error 1.5 e^2 per step: 9e-14, then rounding).  Both arguments in make_rot are
+// normal and positive: dd^2 + 4|g|^2 > 0 once the pair passed the threshold, and c^2 in [1/2, 1].
+__device__ __forceinline__ double rsqrt_nb(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double h = 0.5 * x;
+  double e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  return y;
+}
+
 // Rotation that orthogonalises two rows with squared norms ai, aj and g = x_i . conj(x_j).
 // The rotation ANGLE is computed in FP32 (SFU rsqrt/rcp instead of ~60 dependent FP64 instructions):
 // any tau gives an exactly unitary transformation c [[1, -tau], [conj(tau), 1]] as long as
@@ -86,9 +100,9 @@ __device__ __forceinline__ bool make_rot(double ai, double aj, double gr, double
     // 2r = sqrt(dd^2 + 4|g|^2):  c^2 = 1/2 + |dd|/(4r),  s e = sign(dd) g / (2 r c),
     // t|g| = s|g|/c = sign(dd) |g|^2 / (2 r c^2)  (the amount of squared norm that moves between the rows).
     const double dd = aj - ai;
-    const double rinv = rsqrt(fma(dd, dd, 4.0 * g2));  // 1 / (2r)
+    const double rinv = rsqrt_nb(fma(dd, dd, 4.0 * g2));  // 1 / (2r)
     const double c2 = fma(0.5 * fabs(dd), rinv, 0.5);
-    const double cinv = rsqrt(c2);
+    const double cinv = rsqrt_nb(c2);
     r.cs = c2 * cinv;
     const double ks = copysign(rinv * cinv, dd);
     r.sr = ks * gr;
@@ -146,7 +160,7 @@ template <int NPL, bool FULL>
 __device__ __forceinline__ int pair_smem(cplx *xi, cplx *xj, int N, int lane, double *ni, double *nj, double dead,
                                          double tol2, int rot64) {
   const double ai = *ni, aj = *nj;
-  if (ai <= dead || aj <= dead) return 0;
+  if (__any_sync(0xffffffffu, ai <= dead || aj <= dead)) return 0;  // vote: every lane holds the same norms
   cplx u[NPL], v[NPL];
   double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
 #pragma unroll
@@ -189,7 +203,7 @@ __device__ __forceinline__ int pair_reg(cplx (&u)[NPL], cplx *xj, int N, int lan
 #endif
 ) {
   const double ai = *ni, aj = *nj;
-  if (ai <= dead || aj <= dead) return 0;
+  if (__any_sync(0xffffffffu, ai <= dead || aj <= dead)) return 0;  // vote: every lane holds the same norms
   TCB_T(t0);
   cplx v[NPL];
   double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
@@ -247,7 +261,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
   uint64_t *const barP = reinterpret_cast<uint64_t *>(tail + d.n2 * sizeof(double));
   uint64_t *const barQ = barP + 1;
   int *const s_ver = reinterpret_cast<int *>(barP + 4);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = __reduce_max_sync(0xffffffffu, tid >> 5);  // provably uniform
 #ifdef TCB_TIMING
   long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long tk0 = clock64();
@@ -389,7 +403,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
               do {
                 asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(vaddr + 4 * jq) : "memory");
                 if (++spins > (1ull << 24)) __trap();
-              } while (v < base + s);
+              } while (__any_sync(0xffffffffu, v < base + s));
             }
             TCB_T(tw1);
             TCB_ACC(4, tw0, tw1);
@@ -427,7 +441,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
     }
     if (lane == 0 && nrot) atomicAdd(s_rot, nrot);
     __syncthreads();
-    const int tot = *s_rot;
+    const int tot = __reduce_max_sync(0xffffffffu, *s_rot);
     __syncthreads();
     if (tot == 0) break;
   }
@@ -462,7 +476,10 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) jacobi_blocked_kernel(TcDev d
   Bond b;
   // blockIdx.x = chain, blockIdx.y = rank of the bond in centre-out order (largest matrices first)
   if (!get_bond(d, a, centre_out(blockIdx.y, a.nb), blockIdx.x, b)) return;
-  const int N = b.N, K = b.M < b.N ? b.M : b.N;
+  // sizes come from the chi table in memory: the same in every lane, but only a warp reduction (REDUX) makes them
+  // provably uniform for the compiler -- a branch on a loaded value counts as divergent and every later shuffle then
+  // carries a BRA.DIV divergence check
+  const int N = __reduce_max_sync(0xffffffffu, b.N), K = __reduce_max_sync(0xffffffffu, b.M < b.N ? b.M : b.N);
   cplx *X = d.Xw + b.slot * d.slot_stride;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)3 * BR * d.n2 * sizeof(cplx) + d.n2 * sizeof(double));

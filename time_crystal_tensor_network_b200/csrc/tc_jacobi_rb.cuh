@@ -115,18 +115,8 @@ __device__ __forceinline__ void mbar_wait_u(uint64_t *bar, uint32_t parity) {
         : "memory");
   } while (__any_sync(FULLM, ok == 0));
 }
-// 1/sqrt(x) for normal positive x without the special-case branch of rsqrt(double): hardware seed (MUFU.RSQ64H,
-// ~2^-22) and two Newton steps; the branch would split the basic block just like BRA.DIV.
-__device__ __forceinline__ double rsqrt_nb(double x) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  const double h = 0.5 * x;
-  double e = fma(-h * y, y, 0.5);
-  y = fma(y, e, y);
-  e = fma(-h * y, y, 0.5);
-  y = fma(y, e, y);
-  return y;
-}
+using tcb::rsqrt_nb;
+
 template <int NPL>
 __device__ __forceinline__ void dot_rows(const cplx (&u)[NPL], const cplx (&v)[NPL], double &gr, double &gi) {
   // g = sum u conj(v), four independent accumulation chains
