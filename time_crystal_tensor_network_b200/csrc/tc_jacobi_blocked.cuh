@@ -85,54 +85,26 @@ __device__ __forceinline__ double rsqrt_nb(double x) {
   return y;
 }
 
-// Rotation that orthogonalises two rows with squared norms ai, aj and g = x_i . conj(x_j).
-// The rotation ANGLE is computed in FP32 (SFU rsqrt/rcp instead of ~60 dependent FP64 instructions):
-// any tau gives an exactly unitary transformation c [[1, -tau], [conj(tau), 1]] as long as
-// c = 1/sqrt(1 + |tau|^2) is formed in FP64 from the tau that is actually applied; an FP32-accurate
-// angle only leaves a residual ~1e-7 |g|, which the quadratically convergent sweeps absorb.
-// The norm updates use the exact identities for the applied tau.
-__device__ __forceinline__ bool make_rot(double ai, double aj, double gr, double gi, double tol2, Rot &r,
-                                         int rot64) {
+// Rotation that orthogonalises two rows with squared norms ai, aj and g = x_i . conj(x_j); false when the pair is
+// below the threshold or one of the rows is numerically zero (`alive` false).
+// FP64 set-up with two rsqrt and no division / sqrt / |g|.  With dd = aj - ai and 2r = sqrt(dd^2 + 4|g|^2):
+// c^2 = 1/2 + |dd|/(4r),  s e = sign(dd) g / (2 r c),  t|g| = s|g|/c = sign(dd) |g|^2 / (2 r c^2) (the amount of
+// squared norm that moves between the rows).  (An FP32/SFU angle with an FP64 cosine was measured slower on the
+// B200 and cost a tenth of a sweep; it is gone.)
+__device__ __forceinline__ bool make_rot(bool alive, double ai, double aj, double gr, double gi, double tol2, Rot &r) {
   const double g2 = gr * gr + gi * gi;
-  if (!(g2 > tol2 * ai * aj)) return false;
-  if (rot64) {
-    // FP64 set-up with two rsqrt and no division / sqrt / |g| (default).  With dd = aj - ai and
-    // 2r = sqrt(dd^2 + 4|g|^2):  c^2 = 1/2 + |dd|/(4r),  s e = sign(dd) g / (2 r c),
-    // t|g| = s|g|/c = sign(dd) |g|^2 / (2 r c^2)  (the amount of squared norm that moves between the rows).
-    const double dd = aj - ai;
-    const double rinv = rsqrt_nb(fma(dd, dd, 4.0 * g2));  // 1 / (2r)
-    const double c2 = fma(0.5 * fabs(dd), rinv, 0.5);
-    const double cinv = rsqrt_nb(c2);
-    r.cs = c2 * cinv;
-    const double ks = copysign(rinv * cinv, dd);
-    r.sr = ks * gr;
-    r.si = ks * gi;
-    const double tg = g2 * ks * cinv;
-    r.ni = ai - tg;
-    r.nj = aj + tg;
-    return true;
-  }
-  // scale by an exact power of two so that max(ai, aj) is O(1) in float
-  const double m = fmax(ai, aj);
-  const int hi = __double2hiint(m);
-  const double sc = __hiloint2double((2046 << 20) - (hi & 0x7ff00000), 0);  // 2^-exponent(m)
-  const float fd = (float)((aj - ai) * sc);
-  const float fr = (float)(gr * sc), fi = (float)(gi * sc);
-  const float mx = fmaxf(fabsf(fr), fabsf(fi)), mn = fminf(fabsf(fr), fabsf(fi));
-  const float q = __fdividef(mn, mx);
-  const float iga = __frcp_rn(mx * sqrtf(fmaf(q, q, 1.0f)));  // 1 / |g| (scaled)
-  const float az = 0.5f * fabsf(fd) * iga;                     // |zeta| = |aj - ai| / (2 |g|)
-  float t = az > 1e15f ? __fdividef(0.5f, az) : __frcp_rn(az + sqrtf(fmaf(az, az, 1.0f)));
-  t = copysignf(t, fd);
-  const double tr = (double)(t * (fr * iga)), ti = (double)(t * (fi * iga));  // tau = t (g / |g|): unit phase first, t alone can be 1e-30
-  const double t2 = fma(tr, tr, ti * ti);
-  r.cs = rsqrt(1.0 + t2);
-  r.sr = r.cs * tr;
-  r.si = r.cs * ti;
-  const double c2 = r.cs * r.cs;
-  const double cross = 2.0 * fma(tr, gr, ti * gi);  // 2 Re(conj(tau) g)
-  r.ni = c2 * (ai - cross + t2 * aj);
-  r.nj = c2 * (aj + cross + t2 * ai);
+  if (!(alive && g2 > tol2 * ai * aj)) return false;
+  const double dd = aj - ai;
+  const double rinv = rsqrt_nb(fma(dd, dd, 4.0 * g2));  // 1 / (2r)
+  const double c2 = fma(0.5 * fabs(dd), rinv, 0.5);
+  const double cinv = rsqrt_nb(c2);
+  r.cs = c2 * cinv;
+  const double ks = copysign(rinv * cinv, dd);
+  r.sr = ks * gr;
+  r.si = ks * gi;
+  const double tg = g2 * ks * cinv;
+  r.ni = ai - tg;
+  r.nj = aj + tg;
   return true;
 }
 
@@ -158,9 +130,7 @@ __device__ __forceinline__ void warp_sum2(double &a, double &b) {
 // both rows in shared memory (internal pairs of a block)
 template <int NPL, bool FULL>
 __device__ __forceinline__ int pair_smem(cplx *xi, cplx *xj, int N, int lane, double *ni, double *nj, double dead,
-                                         double tol2, int rot64) {
-  const double ai = *ni, aj = *nj;
-  if (__any_sync(0xffffffffu, ai <= dead || aj <= dead)) return 0;  // vote: every lane holds the same norms
+                                         double tol2) {
   cplx u[NPL], v[NPL];
   double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
 #pragma unroll
@@ -173,10 +143,11 @@ __device__ __forceinline__ int pair_smem(cplx *xi, cplx *xj, int N, int lane, do
     h0 = fma(u[e].y, v[e].x, h0);
     h1 = fma(-u[e].x, v[e].y, h1);
   }
+  const double ai = *ni, aj = *nj;
   double gr = g0 + g1, gi = h0 + h1;
   warp_sum2(gr, gi);
   Rot r;
-  if (!make_rot(ai, aj, gr, gi, tol2, r, rot64)) return 0;
+  if (!make_rot(ai > dead && aj > dead, ai, aj, gr, gi, tol2, r)) return 0;
   const int big = (gr * gr + gi * gi) > tcj::SMALL_REL2 * ai * aj;
 #pragma unroll
   for (int e = 0; e < NPL; ++e) {
@@ -194,16 +165,15 @@ __device__ __forceinline__ int pair_smem(cplx *xi, cplx *xj, int N, int lane, do
   return big;
 }
 
-// row i in registers (u), row j in shared memory
+// row i in registers (u, its squared norm ai too), row j in shared memory.  The row is loaded before anything is
+// decided: its LDS latency overlaps the norm load, and a numerically zero row (rare) just costs its dot product.
 template <int NPL, bool FULL>
-__device__ __forceinline__ int pair_reg(cplx (&u)[NPL], cplx *xj, int N, int lane, double *ni, double *nj, double dead,
-                                        double tol2, int rot64
+__device__ __forceinline__ int pair_reg(cplx (&u)[NPL], cplx *xj, int N, int lane, double &ai, double *nj, double dead,
+                                        double tol2
 #ifdef TCB_TIMING
                                         , long long (&tacc)[8]
 #endif
 ) {
-  const double ai = *ni, aj = *nj;
-  if (__any_sync(0xffffffffu, ai <= dead || aj <= dead)) return 0;  // vote: every lane holds the same norms
   TCB_T(t0);
   cplx v[NPL];
   double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
@@ -216,6 +186,7 @@ __device__ __forceinline__ int pair_reg(cplx (&u)[NPL], cplx *xj, int N, int lan
     h0 = fma(u[e].y, v[e].x, h0);
     h1 = fma(-u[e].x, v[e].y, h1);
   }
+  const double aj = *nj;
   double gr = g0 + g1, gi = h0 + h1;
   TCB_T(t1);
   warp_sum2(gr, gi);
@@ -226,7 +197,7 @@ __device__ __forceinline__ int pair_reg(cplx (&u)[NPL], cplx *xj, int N, int lan
   tacc[6] += 1;
 #endif
   Rot r;
-  if (!make_rot(ai, aj, gr, gi, tol2, r, rot64)) return 0;
+  if (!make_rot(ai > dead && aj > dead, ai, aj, gr, gi, tol2, r)) return 0;
   const int big = (gr * gr + gi * gi) > tcj::SMALL_REL2 * ai * aj;
   TCB_T(t3);
 #pragma unroll
@@ -235,10 +206,8 @@ __device__ __forceinline__ int pair_reg(cplx (&u)[NPL], cplx *xj, int N, int lan
     rot_apply(u[e], v[e], r);
     if (FULL || c < N) xj[c] = v[e];
   }
-  if (lane == 0) {
-    *ni = r.ni;
-    *nj = r.nj;
-  }
+  ai = r.ni;
+  if (lane == 0) *nj = r.nj;
   TCB_T(t4);
   TCB_ACC(2, t2, t3);
   TCB_ACC(3, t3, t4);
@@ -272,7 +241,6 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
   const uint32_t row_bytes = (uint32_t)N * sizeof(cplx);
   uint32_t phP = 0, phQ0 = 0, phQ1 = 0;  // scalars, not arrays: dynamic indexing would put them in local memory
   int verBase0 = 0, verBase1 = 0;
-  const int rot64 = d.rot64 & 1;
   const bool lockstep = (d.rot64 & 2) != 0;
   double dead = 0.0;
   int sweep = 0;
@@ -333,8 +301,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
           if (r < rowsB - 1 && wl < rowsB / 2) {
             int i, j;
             tcj::rr_pair(rowsB, r, wl, i, j);
-            nrot += pair_smem<NPL, FULL>(blk + (size_t)i * N, blk + (size_t)j * N, N, lane, nb + i, nb + j, dead, tol2,
-                                         rot64);
+            nrot += pair_smem<NPL, FULL>(blk + (size_t)i * N, blk + (size_t)j * N, N, lane, nb + i, nb + j, dead, tol2);
           }
           __syncthreads();
         }
@@ -347,6 +314,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
         const int c = lane + 32 * e;
         u[e] = (haveP && (FULL || c < N)) ? sP[(size_t)warp * N + c] : cmake(0.0, 0.0);
       }
+      double aP = haveP ? s_nrm2[p * BR + warp] : 0.0;  // squared norm of the stationary row, in a register for the visits
       // ---- every later block streams through Q
       for (int q = p + 1; q < nblk; ++q) {
         const int buf = (q - p - 1) & 1;
@@ -375,8 +343,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
             if (s == BR / 2) prefetch_next();
             const int jq = (warp + s) & (BR - 1);
             if (haveP && jq < rowsQ)
-              nrot += pair_reg<NPL, FULL>(u, Q + (size_t)jq * N, N, lane, s_nrm2 + p * BR + warp,
-                                          s_nrm2 + q * BR + jq, dead, tol2, rot64
+              nrot += pair_reg<NPL, FULL>(u, Q + (size_t)jq * N, N, lane, aP, s_nrm2 + q * BR + jq, dead, tol2
 #ifdef TCB_TIMING
                                           , tacc
 #endif
@@ -408,8 +375,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
             TCB_T(tw1);
             TCB_ACC(4, tw0, tw1);
             if (haveP && jq < rowsQ)
-              nrot += pair_reg<NPL, FULL>(u, Q + (size_t)jq * N, N, lane, s_nrm2 + p * BR + warp,
-                                          s_nrm2 + q * BR + jq, dead, tol2, rot64
+              nrot += pair_reg<NPL, FULL>(u, Q + (size_t)jq * N, N, lane, aP, s_nrm2 + q * BR + jq, dead, tol2
 #ifdef TCB_TIMING
                                           , tacc
 #endif
@@ -429,6 +395,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
       }
       // ---- block p back to global
       if (haveP) {
+        if (lane == 0) s_nrm2[p * BR + warp] = aP;
 #pragma unroll
         for (int e = 0; e < NPL; ++e) {
           const int c = lane + 32 * e;
