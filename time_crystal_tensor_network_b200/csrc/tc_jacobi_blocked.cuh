@@ -58,13 +58,27 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 #ifdef TCB_TIMING
 // phase timers (diagnostic build only): [0] load+dot, [1] warp reduction, [2] rotation set-up, [3] rotate+store,
-// [4] hand-over wait / barrier, [5] pairs rotated, [6] pairs visited, [7] whole kernel (warp 0 of K=256 matrices)
+// [4] hand-over wait / barrier, [5] pairs rotated, [6] pairs visited, [7] whole kernel (warp 3 of K=256 matrices).
+// With -DTCB_COARSE the same slots hold the coarse phases of a sweep instead: [0] row norms at the sweep start,
+// [1] wait for the P block, [2] internal pairs, [3] wait for a q block, [4] the 16 rounds of a visit,
+// [5] end-of-visit fence + barrier + store, [6] P block back to global.
 __device__ unsigned long long g_tcb_timing[8];
+#ifdef TCB_COARSE
+#define TCB_T(var)
+#define TCB_ACC(k, a, b)
+#define TCC_T(var) const long long var = clock64()
+#define TCC_ACC(k, a, b) tacc[k] += (b) - (a)
+#else
 #define TCB_T(var) const long long var = clock64()
 #define TCB_ACC(k, a, b) tacc[k] += (b) - (a)
+#define TCC_T(var)
+#define TCC_ACC(k, a, b)
+#endif
 #else
 #define TCB_T(var)
 #define TCB_ACC(k, a, b)
+#define TCC_T(var)
+#define TCC_ACC(k, a, b)
 #endif
 
 struct Rot {
@@ -119,12 +133,18 @@ __device__ __forceinline__ void rot_apply(cplx &u, cplx &v, const Rot &r) {
   v = vn;
 }
 
+// sums of a and b over the warp, in every lane.  Packed butterfly: after the first exchange the low half-warp carries
+// the partial sums of a and the high half those of b, so rounds 2..5 move one double instead of two; a last exchange
+// hands each half the other total (6 shuffles + 5 adds instead of 10 + 10).
 __device__ __forceinline__ void warp_sum2(double &a, double &b) {
+  const bool hi = (threadIdx.x & 16) != 0;
+  double k = hi ? b : a;
+  k += __shfl_xor_sync(0xffffffffu, hi ? a : b, 16);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, o);
-    b += __shfl_xor_sync(0xffffffffu, b, o);
-  }
+  for (int o = 8; o > 0; o >>= 1) k += __shfl_xor_sync(0xffffffffu, k, o);
+  const double other = __shfl_xor_sync(0xffffffffu, k, 16);
+  a = hi ? other : k;
+  b = hi ? k : other;
 }
 
 // both rows in shared memory (internal pairs of a block)
@@ -246,6 +266,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
   int sweep = 0;
   for (; sweep < tcj::MAX_SWEEPS; ++sweep) {
     // all bulk stores of the previous sweep must have landed before rows are re-read
+    TCC_T(c0);
     if (tid == 0) bulk_wait_all();
     __syncthreads();
     for (int r = warp; r < K; r += NW) {
@@ -263,7 +284,10 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
       dead = tcj::DEAD_REL2 * block_sum(p, red);
     }
     int nrot = 0;
+    TCC_T(c1);
+    TCC_ACC(0, c0, c1);
     for (int p = 0; p < nblk; ++p) {
+      TCC_T(c2);
       const int rowsP = min(BR, K - p * BR);
       cplx *gP = X + (size_t)p * BR * N;
       if (tid == 0) {
@@ -278,6 +302,8 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
       }
       mbar_wait(barP, phP);
       phP ^= 1;
+      TCC_T(c3);
+      TCC_ACC(1, c2, c3);
       // ---- internal pairs: circle method on the rows of a block, one pair per warp, BR/2 warps per block.
       // Blocks are handled two at a time (p even: block p in P on warps 0..BR/2-1 and block p+1, already
       // prefetched into stage 0, on warps BR/2..BR-1) so that no warp idles; any order of the pairs within a
@@ -306,6 +332,8 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
           __syncthreads();
         }
       }
+      TCC_T(c4);
+      TCC_ACC(2, c3, c4);
       // ---- row p_w into registers
       cplx u[NPL];
       const bool haveP = warp < rowsP;
@@ -330,6 +358,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
                       &barQ[buf ^ 1]);
           }
         };
+        TCC_T(c5);
         if (!(q == p + 1 && q0_ready)) {  // stage 0 of the first visit may already have been consumed above
           mbar_wait(&barQ[buf], buf ? phQ1 : phQ0);
           if (buf)
@@ -338,6 +367,8 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
             phQ0 ^= 1;
         }
         cplx *Q = (sQ + (size_t)buf * BR * N);
+        TCC_T(c6);
+        TCC_ACC(3, c5, c6);
         if (lockstep) {
           for (int s = 0; s < BR; ++s) {
             if (s == BR / 2) prefetch_next();
@@ -389,10 +420,15 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
           else
             verBase0 = base + BR;
         }
+        TCC_T(c7);
+        TCC_ACC(4, c6, c7);
         fence_async_smem();
         __syncthreads();
         if (tid == 0) bulk_store(X + (size_t)q * BR * N, Q, rowsQ * row_bytes);
+        TCC_T(c8);
+        TCC_ACC(5, c7, c8);
       }
+      TCC_T(c9);
       // ---- block p back to global
       if (haveP) {
         if (lane == 0) s_nrm2[p * BR + warp] = aP;
@@ -405,6 +441,8 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
       fence_async_smem();
       __syncthreads();
       if (tid == 0) bulk_store(gP, sP, rowsP * row_bytes);
+      TCC_T(c10);
+      TCC_ACC(6, c9, c10);
     }
     if (lane == 0 && nrot) atomicAdd(s_rot, nrot);
     __syncthreads();
