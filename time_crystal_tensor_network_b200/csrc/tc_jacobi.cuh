@@ -144,10 +144,18 @@ __global__ void __launch_bounds__(NT) qr_kernel(TcDev d, LayerArgs a) {
 //   panel:    one row per thread, the panel row in registers; per column one batched block reduction
 //             (|x|^2 and the v^H a products for the remaining panel columns); reflectors V to smem
 //   T:        compact WY factor, H_0 ... H_{QB-1} = I - V T V^H (larft forward/columnwise)
-//   trailing: thread per column, W = V^H A (one pass), W <- T^H W, A -= V W (second pass):
-//             two passes over the trailing matrix per PANEL instead of per column.
+//   trailing: warp per tile of 8 columns on the FP64 tensor pipe (DMMA): W = V^H A (one pass), W <- T^H W,
+//             A -= V W (second pass): two passes over the trailing matrix per PANEL instead of per column.
 // static smem: V 32 KB + reduction scratch
 // ------------------------------------------------------------------------------------------------
+// FP64 tensor-pipe MMA (8 x 4) x (4 x 8): A fragment element [lane >> 2][lane & 3], B fragment [lane & 3][lane >> 2],
+// accumulator [lane >> 2][2 (lane & 3), + 1]
+__device__ __forceinline__ void tcg_dmma(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
 constexpr int QB = 8, QNT = 256, QMAXM = 256;  // fast-path instance: M <= 256 rows, 256 threads
 constexpr int QNTW = 512, QMAXMW = 512;         // wide instance (chi_cap <= 256): M <= 512 rows, 512 threads
 
@@ -276,35 +284,68 @@ __global__ void __launch_bounds__(QT) qr_blocked_kernel(TcDev d, LayerArgs a) {
       }
       __syncthreads();
     }
-    // ---- trailing columns: A <- (I - V T^H V^H) A
-    const int c = k0 + QB + tid;
-    if (c < N) {
-      cplx *col = X + (size_t)k0 * N + c;
-      cplx W[QB];
+    // ---- trailing columns: A <- (I - V T^H V^H) A on the FP64 tensor pipe (mma.sync m8n8k4.f64 = DMMA; same FP64
+    // peak as DFMA on sm_100a, but one warp instruction per 256 FMAs and no shared-memory broadcast per FMA).
+    // A warp owns tiles of 8 trailing columns.  Pass 1, W = V^H A: M = 8 reflectors, K = rows, N = 8 columns (A operand
+    // conj(V)^T from shared memory, B operand the trailing matrix straight from L2).  W2 = T^H W per lane from a per-warp
+    // scratch, directly in the B-operand layout of pass 2, A -= V W2: M = 8 rows, K = 8 reflectors, N = 8 columns.
+    {
+      __shared__ __align__(16) cplx Wsm[(QT / 32) * 64];
+      const int lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fk = lane & 3;
+      const int ncols = N - (k0 + QB);
+      const int ntiles = (ncols + 7) / 8;
+      cplx *At = X + (size_t)k0 * N + k0 + QB;  // trailing block: row r (relative to k0), column cc (relative to k0 + QB)
+      cplx *Ws = Wsm + warp * 64;
+      for (int ct = warp; ct < ntiles; ct += QT / 32) {
+        const int c0 = ct * 8;
+        const bool cok = c0 + fr < ncols;
+        double wre[2] = {0.0, 0.0}, wim[2] = {0.0, 0.0};
+#pragma unroll 4
+        for (int r0 = 0; r0 < rows; r0 += 4) {
+          const int r = r0 + fk;
+          const bool rok = r < rows;
+          const cplx av = (cok && rok) ? At[(size_t)r * N + c0 + fr] : cmake(0.0, 0.0);
+          const cplx v = rok ? V[r * QB + fr] : cmake(0.0, 0.0);
+          tcg_dmma(wre[0], wre[1], v.x, av.x);  // conj(v) a = (vx ax + vy ay) + i (vx ay - vy ax)
+          tcg_dmma(wre[0], wre[1], v.y, av.y);
+          tcg_dmma(wim[0], wim[1], v.x, av.y);
+          tcg_dmma(wim[0], wim[1], -v.y, av.x);
+        }
+        // C layout: this lane holds W[j = fr][c = 2 fk, 2 fk + 1]
+        Ws[fr * 8 + 2 * fk] = cmake(wre[0], wim[0]);
+        Ws[fr * 8 + 2 * fk + 1] = cmake(wre[1], wim[1]);
+        __syncwarp();
+        cplx w2[2];  // W2[i = 4 kc + fk][c = fr] = sum_{j <= i} conj(T[j][i]) W[j][c]
 #pragma unroll
-      for (int j = 0; j < QB; ++j) W[j] = cmake(0.0, 0.0);
-      for (int r = 0; r < rows; ++r) {
-        const cplx av = col[(size_t)r * N];
-        const cplx *vr = V + r * QB;
+        for (int kc = 0; kc < 2; ++kc) {
+          const int i = 4 * kc + fk;
+          cplx acc = cmake(0.0, 0.0);
 #pragma unroll
-        for (int j = 0; j < QB; ++j) cfmac(W[j], vr[j], av);
-      }
-      cplx W2[QB];
+          for (int j = 0; j < QB; ++j)
+            if (j <= i) cfmac(acc, Tm[j * QB + i], Ws[j * 8 + fr]);
+          w2[kc] = acc;
+        }
+        __syncwarp();
+        const int cc = c0 + 2 * fk;
+#pragma unroll 2
+        for (int r0 = 0; r0 < rows; r0 += 8) {
+          const int r = r0 + fr;
+          const bool rok = r < rows;
+          cplx *ap = At + (size_t)r * N + cc;
+          const cplx a0 = (rok && cc < ncols) ? ap[0] : cmake(0.0, 0.0);
+          const cplx a1 = (rok && cc + 1 < ncols) ? ap[1] : cmake(0.0, 0.0);
+          double cre[2] = {a0.x, a1.x}, cim[2] = {a0.y, a1.y};
 #pragma unroll
-      for (int i = 0; i < QB; ++i) {
-        cplx acc = cmake(0.0, 0.0);
-#pragma unroll
-        for (int j = 0; j < QB; ++j)
-          if (j <= i) cfmac(acc, Tm[j * QB + i], W[j]);
-        W2[i] = acc;
-      }
-      for (int r = 0; r < rows; ++r) {
-        cplx av = col[(size_t)r * N];
-        const cplx *vr = V + r * QB;
-        cplx acc = cmake(0.0, 0.0);
-#pragma unroll
-        for (int j = 0; j < QB; ++j) cfma(acc, vr[j], W2[j]);
-        col[(size_t)r * N] = csub(av, acc);
+          for (int kc = 0; kc < 2; ++kc) {
+            const cplx v = rok ? V[r * QB + 4 * kc + fk] : cmake(0.0, 0.0);
+            tcg_dmma(cre[0], cre[1], -v.x, w2[kc].x);  // a - v w2
+            tcg_dmma(cre[0], cre[1], v.y, w2[kc].y);
+            tcg_dmma(cim[0], cim[1], -v.x, w2[kc].y);
+            tcg_dmma(cim[0], cim[1], -v.y, w2[kc].x);
+          }
+          if (rok && cc < ncols) ap[0] = cmake(cre[0], cim[0]);
+          if (rok && cc + 1 < ncols) ap[1] = cmake(cre[1], cim[1]);
+        }
       }
     }
     __syncthreads();
