@@ -183,15 +183,9 @@ def run_reference(a):
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def ncu_traffic_gb():
-    """DRAM bytes of the dominant kernel from the committed ncu capture (None if the file is missing)."""
-    path = os.path.join(ROOT, 'profiles', 'r01_jacobi_blocked_ncu_metrics.txt')
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (None if the file is missing)."""
     try:
-        tot = 0.0
-        for line in open(path):
-            for key in ('dram__bytes_read.sum [Gbyte] = ', 'dram__bytes_write.sum [Gbyte] = '):
-                if line.startswith(key):
-                    tot += float(line[len(key):])
-        return tot or None
+        return float(json.load(open(os.path.join(ROOT, 'profiles', 'ncu_dominant_kernel.json')))['dram_gb_per_launch'])
     except Exception:
         return None
 
@@ -332,7 +326,7 @@ def run_ours(a):
                 'frac': (achieved / fp64_peak) if achieved else None,
                 'traffic': ncu_traffic_gb(),
                 'traffic_unit': 'GB per Jacobi launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full capture '
-                                'of a 32-chain layer, profiles/r01_jacobi_blocked_ncu_metrics.txt); algorithmic: 0.8 GB',
+                                'of a 32-chain layer, profiles/r01d_ncu_kernels.txt); algorithmic: 0.8 GB',
                 'peak_source': 'tc_probe_fp64 (DFMA chain, all SMs) measured in this run; MEASURED_PEAKS.json has no '
                                f'FP64 entry (hbm_gbs={peaks.get("hbm_gbs")}); DMMA probe {dmma_peak:.1f} TFLOP/s',
                 'flops_model': 'SURVEY 8d: 4(4m^2 n + 8 m n^2 + 9 n^3) per update, summed over the actual bond '
