@@ -82,6 +82,12 @@ __global__ void __launch_bounds__(LB, 1) k(double *out, int iters, double seed) 
   RotP rA, rB;
   rA.cs = rB.cs = 0.8; rA.sr = rB.sr = 0.36; rA.si = rB.si = 0.48;
   int acc = 0;
+#ifdef STAGGER
+  {  // de-phase the warps: warp w starts w * STAGGER cycles late
+    const long long tw = clock64() + (long long)(threadIdx.x >> 5) * STAGGER;
+    while (clock64() < tw) {}
+  }
+#endif
   long long t0 = clock64();
   for (int it = 0; it < iters; ++it) {
     if (MODE == 0) {
@@ -113,7 +119,7 @@ __global__ void __launch_bounds__(LB, 1) k(double *out, int iters, double seed) 
       dot_rows<8>(uA, vA, gr, gi);
       tcb::warp_sum2(gr, gi);
       tcb::Rot r;
-      if (tcb::make_rot(aA, bA, gr, gi, 1e-40, r, 1)) {
+      if (tcb::make_rot(true, aA, bA, gr, gi, 1e-40, r)) {
         rot_rows<8>(uA, vA, r.cs, r.sr, r.si);
         aA = r.ni;
         bA = r.nj;
