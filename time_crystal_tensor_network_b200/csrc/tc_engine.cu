@@ -514,7 +514,7 @@ static int measure_into(tc_ctx *c, double *rdm, double *Z, double *ent, double *
     LAUNCHED();
   }
   if (ov) {
-    tco::overlap_product_kernel<<<d.R, tco::NT, 2 * d.chi_cap * sizeof(cplx), c->stream>>>(d, ov);
+    tco::overlap_product_kernel<<<d.R, tco::NT, (2 * d.chi_cap + (tco::NT / 32) * tco::OVC) * sizeof(cplx), c->stream>>>(d, ov);
     LAUNCHED();
   }
   if (chi) {
