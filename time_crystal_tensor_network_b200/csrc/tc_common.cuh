@@ -56,7 +56,7 @@ struct TcDev {
   // model
   const cplx *gates;  // [R][L-1][16]
   const cplx *kick;   // [R][4]
-  int rot64;          // Jacobi rotation angle in FP64 instead of FP32 (A/B switch)
+  int rot64;          // TC_ROT64 A/B switches of the Jacobi kernel: bit 1 = barrier per round instead of the row hand-over
   int gates_diag;     // every gate of the model is diagonal (fused phase epilogue)
   double *trunc_err;  // [R][L+1] discarded weight accumulated per bond (single writer, deterministic)
   int *flags;         // [0]: chi_cap overflow count, [1]: Jacobi non-convergence count, [2]: sweeps max

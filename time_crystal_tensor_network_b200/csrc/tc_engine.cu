@@ -607,7 +607,7 @@ int tc_ctx_create(int device, int L, int chi_cap, int R, void *arena, size_t are
   d.gates = c->gates_dev;
   d.kick = c->kick_dev;
   d.gates_diag = 0;
-  d.rot64 = 1;  // bit0: FP64 rotation angle (measured faster than the FP32/SFU variant on B200); bit1: lockstep rounds
+  d.rot64 = 1;  // bit 0: unused (the FP32 angle variant is gone); bit 1: lock-step rounds (barrier instead of hand-over)
   if (const char *e = getenv("TC_ROT64")) d.rot64 = atoi(e);
   d.trunc_err = (double *)(base + lo.trunc_err);
   d.flags = (int *)(base + lo.flags);

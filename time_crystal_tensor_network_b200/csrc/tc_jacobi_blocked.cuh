@@ -6,9 +6,12 @@
 // Sweep = for every block p: stage p, rotate its internal pairs, then keep row p_w in the registers of
 // warp w while every later block q streams through a double-buffered shared-memory stage:
 //   round s of visit (p, q): warp w rotates (p_w, q_{(w+s) mod 16}); q rows are read from and written
-//   back to shared memory, p rows never leave registers; one __syncthreads per round.
+//   back to shared memory, p rows never leave registers; rows pass from warp to warp through per-row
+//   version counters (acquire / release), a barrier per round only with TC_ROT64 bit 1.
 // While visit (p, q) computes, the bulk load of q+1 and the bulk store of q-1 are in flight.
-// Per pair: 4 KB LDS + 4 KB STS, ~100 DFMA per lane; L2 traffic per sweep ~ (K/16)^2/2 blocks.
+// Per pair: 4 KB LDS + 4 KB STS and 167 FP64 instructions per lane (32 dot, 96 rotation, ~39 reduction and set-up:
+// the minimum for standard rotations), 271 SASS instructions in all; L2 traffic per sweep ~ (K/16)^2/2 blocks.
+// ncu (profiles/r01d_ncu_kernels.txt): FP64 pipe 51 % busy, shared-memory wavefronts 49 %, issue slots 46 %.
 #pragma once
 #include "tc_common.cuh"
 #include "tc_jacobi.cuh"
