@@ -28,6 +28,7 @@ EPS = np.finfo(float).eps
 DEAD_REL2 = 1e-30          # rows with |x|^2 < DEAD_REL2 |theta|_F^2 are numerically zero (tc_jacobi.cuh)
 MAX_SWEEPS = 48
 SMALL_REL2 = 1e-16       # a sweep whose rotations were all below 1e-8 relative ends the iteration
+THRESHOLDS = (1e-2, 1e-3, 1e-4, 1e-6)   # tc_jacobi_blocked.cuh: sweeps 0..3 rotate only pairs with |g|^2/(a_i a_j) above
 
 
 def interleave_perm(chi_r):
@@ -77,10 +78,12 @@ def rr_pairs(M, r):
     return np.array(I), np.array(J)
 
 
-def jacobi_rows(X, tol=None, max_sweeps=MAX_SWEEPS):
+def jacobi_rows(X, tol=None, max_sweeps=MAX_SWEEPS, thresholds=()):
     """K2b: one-sided Jacobi on rows.  Returns (X with mutually orthogonal rows, rotations per sweep).
     A pair rotates when |g|^2 > tol^2 a_i a_j, g = x_i . conj(x_j); rotation
-    x_i' = c x_i - (s e) x_j, x_j' = conj(s e) x_i + c x_j with e = g/|g| (same formulas as the kernels)."""
+    x_i' = c x_i - (s e) x_j, x_j' = conj(s e) x_i + c x_j with e = g/|g| (same formulas as the kernels).
+    ``thresholds`` (the 16-warp kernel uses THRESHOLDS): sweep k < len(thresholds) rotates only the pairs with
+    |g|^2 > thresholds[k] a_i a_j; such a sweep cannot end the iteration while any pair is above the tolerance."""
     X = np.array(X, dtype=complex)
     M, N = X.shape
     if M % 2:
@@ -92,16 +95,19 @@ def jacobi_rows(X, tol=None, max_sweeps=MAX_SWEEPS):
     for _sweep in range(max_sweeps):
         nrm2 = np.sum(np.abs(X) ** 2, axis=1)
         nrot = nbig = 0
+        thr2 = max(tol * tol, thresholds[_sweep]) if _sweep < len(thresholds) else tol * tol
+        small2 = tol * tol if thr2 > tol * tol else SMALL_REL2
         for r in range(M - 1):
             I, J = rr_pairs(M, r)
             ai, aj = nrm2[I], nrm2[J]
             g = np.sum(X[I] * X[J].conj(), axis=1)
-            act = (ai > dead) & (aj > dead) & (np.abs(g) ** 2 > tol * tol * ai * aj)
+            alive = (ai > dead) & (aj > dead)
+            nbig += int(np.sum(alive & (np.abs(g) ** 2 > small2 * ai * aj)))
+            act = alive & (np.abs(g) ** 2 > thr2 * ai * aj)
             if not act.any():
                 continue
             I, J, g, ai, aj = I[act], J[act], g[act], ai[act], aj[act]
             ga = np.abs(g)
-            nbig += int(np.sum(ga * ga > SMALL_REL2 * ai * aj))
             dd = aj - ai
             t = np.copysign(2 * ga / (np.abs(dd) + np.sqrt(dd * dd + 4 * ga * ga)), dd)
             cs = 1 / np.sqrt(1 + t * t)

@@ -609,6 +609,15 @@ int tc_ctx_create(int device, int L, int chi_cap, int R, void *arena, size_t are
   d.gates_diag = 0;
   d.rot64 = 1;  // bit 0: unused (the FP32 angle variant is gone); bit 1: lock-step rounds (barrier instead of hand-over)
   if (const char *e = getenv("TC_ROT64")) d.rot64 = atoi(e);
+  {  // threshold schedule of the Jacobi sweeps 0..3; TC_THRESH=0 switches it off, TC_THRESH=a,b,c,d sets it (A/B)
+    double sched[4] = {1e-2, 1e-3, 1e-4, 1e-6};
+    if (const char *e = getenv("TC_THRESH")) {
+      double v[4] = {0.0, 0.0, 0.0, 0.0};
+      sscanf(e, "%lf,%lf,%lf,%lf", &v[0], &v[1], &v[2], &v[3]);
+      for (int k = 0; k < 4; ++k) sched[k] = v[k];
+    }
+    for (int k = 0; k < 4; ++k) d.thr_sched[k] = sched[k];
+  }
   d.trunc_err = (double *)(base + lo.trunc_err);
   d.flags = (int *)(base + lo.flags);
   d.Cw = (cplx *)(base + lo.Cw);

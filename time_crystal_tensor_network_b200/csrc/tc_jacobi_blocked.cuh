@@ -108,9 +108,13 @@ __device__ __forceinline__ double rsqrt_nb(double x) {
 // c^2 = 1/2 + |dd|/(4r),  s e = sign(dd) g / (2 r c),  t|g| = s|g|/c = sign(dd) |g|^2 / (2 r c^2) (the amount of
 // squared norm that moves between the rows).  (An FP32/SFU angle with an FP64 cosine was measured slower on the
 // B200 and cost a tenth of a sweep; it is gone.)
-__device__ __forceinline__ bool make_rot(bool alive, double ai, double aj, double gr, double gi, double tol2, Rot &r) {
+__device__ __forceinline__ bool make_rot(bool alive, double ai, double aj, double gr, double gi, double thr2,
+                                         double small2, Rot &r, int &big) {
   const double g2 = gr * gr + gi * gi;
-  if (!(alive && g2 > tol2 * ai * aj)) return false;
+  const double aa = ai * aj;
+  // `big` = the pair keeps the iteration going (stopping rule), whether or not this sweep rotates it
+  big = alive && g2 > small2 * aa;
+  if (!(alive && g2 > thr2 * aa)) return false;
   const double dd = aj - ai;
   const double rinv = rsqrt_nb(fma(dd, dd, 4.0 * g2));  // 1 / (2r)
   const double c2 = fma(0.5 * fabs(dd), rinv, 0.5);
@@ -153,7 +157,7 @@ __device__ __forceinline__ void warp_sum2(double &a, double &b) {
 // both rows in shared memory (internal pairs of a block)
 template <int NPL, bool FULL>
 __device__ __forceinline__ int pair_smem(cplx *xi, cplx *xj, int N, int lane, double *ni, double *nj, double dead,
-                                         double tol2) {
+                                         double tol2, double small2) {
   cplx u[NPL], v[NPL];
   double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
 #pragma unroll
@@ -170,8 +174,8 @@ __device__ __forceinline__ int pair_smem(cplx *xi, cplx *xj, int N, int lane, do
   double gr = g0 + g1, gi = h0 + h1;
   warp_sum2(gr, gi);
   Rot r;
-  if (!make_rot(ai > dead && aj > dead, ai, aj, gr, gi, tol2, r)) return 0;
-  const int big = (gr * gr + gi * gi) > tcj::SMALL_REL2 * ai * aj;
+  int big;
+  if (!make_rot(ai > dead && aj > dead, ai, aj, gr, gi, tol2, small2, r, big)) return big;
 #pragma unroll
   for (int e = 0; e < NPL; ++e) {
     const int c = lane + 32 * e;
@@ -192,7 +196,7 @@ __device__ __forceinline__ int pair_smem(cplx *xi, cplx *xj, int N, int lane, do
 // decided: its LDS latency overlaps the norm load, and a numerically zero row (rare) just costs its dot product.
 template <int NPL, bool FULL>
 __device__ __forceinline__ int pair_reg(cplx (&u)[NPL], cplx *xj, int N, int lane, double &ai, double *nj, double dead,
-                                        double tol2
+                                        double tol2, double small2
 #ifdef TCB_TIMING
                                         , long long (&tacc)[8]
 #endif
@@ -220,8 +224,8 @@ __device__ __forceinline__ int pair_reg(cplx (&u)[NPL], cplx *xj, int N, int lan
   tacc[6] += 1;
 #endif
   Rot r;
-  if (!make_rot(ai > dead && aj > dead, ai, aj, gr, gi, tol2, r)) return 0;
-  const int big = (gr * gr + gi * gi) > tcj::SMALL_REL2 * ai * aj;
+  int big;
+  if (!make_rot(ai > dead && aj > dead, ai, aj, gr, gi, tol2, small2, r, big)) return big;
   TCB_T(t3);
 #pragma unroll
   for (int e = 0; e < NPL; ++e) {
@@ -260,7 +264,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
 #endif
   const int nblk = (K + BR - 1) / BR;
   const double tol = 2.0 * sqrt((double)N) * 2.220446049250313e-16;
-  const double tol2 = tol * tol;
+  const double tol2_final = tol * tol;
   const uint32_t row_bytes = (uint32_t)N * sizeof(cplx);
   uint32_t phP = 0, phQ0 = 0, phQ1 = 0;  // scalars, not arrays: dynamic indexing would put them in local memory
   int verBase0 = 0, verBase1 = 0;
@@ -286,6 +290,15 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
       for (int r = tid; r < K; r += NT) p += s_nrm2[r];
       dead = tcj::DEAD_REL2 * block_sum(p, red);
     }
+    // threshold Jacobi: the early sweeps rotate only the pairs that are far from orthogonal (|g|^2 / (a_i a_j) above
+    // 1e-2, 1e-3, 1e-4, 1e-6 in sweeps 0..3); a small rotation made now is undone by the large ones around it and has
+    // to be made again.  Same final accuracy and sweep count, a fifth fewer rotations (NumPy model on TEBD matrices).
+    // The parameter of the pair functions called tol2 is this sweep's rotation threshold from here on.
+    const double tol2 = sweep < 4 ? fmax(tol2_final, d.thr_sched[sweep]) : tol2_final;
+    // stopping rule: a sweep that rotated every pair above the final tolerance and found them all below 1e-8 ends the
+    // iteration (quadratic convergence: what is left is below 1e-16); a threshold sweep has skipped pairs, so there
+    // anything above the final tolerance keeps the iteration going
+    const double small2 = tol2 > tol2_final ? tol2_final : tcj::SMALL_REL2;
     int nrot = 0;
     TCC_T(c1);
     TCC_ACC(0, c0, c1);
@@ -330,7 +343,8 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
           if (r < rowsB - 1 && wl < rowsB / 2) {
             int i, j;
             tcj::rr_pair(rowsB, r, wl, i, j);
-            nrot += pair_smem<NPL, FULL>(blk + (size_t)i * N, blk + (size_t)j * N, N, lane, nb + i, nb + j, dead, tol2);
+            nrot += pair_smem<NPL, FULL>(blk + (size_t)i * N, blk + (size_t)j * N, N, lane, nb + i, nb + j, dead, tol2,
+                                         small2);
           }
           __syncthreads();
         }
@@ -377,7 +391,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
             if (s == BR / 2) prefetch_next();
             const int jq = (warp + s) & (BR - 1);
             if (haveP && jq < rowsQ)
-              nrot += pair_reg<NPL, FULL>(u, Q + (size_t)jq * N, N, lane, aP, s_nrm2 + q * BR + jq, dead, tol2
+              nrot += pair_reg<NPL, FULL>(u, Q + (size_t)jq * N, N, lane, aP, s_nrm2 + q * BR + jq, dead, tol2, small2
 #ifdef TCB_TIMING
                                           , tacc
 #endif
@@ -409,7 +423,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
             TCB_T(tw1);
             TCB_ACC(4, tw0, tw1);
             if (haveP && jq < rowsQ)
-              nrot += pair_reg<NPL, FULL>(u, Q + (size_t)jq * N, N, lane, aP, s_nrm2 + q * BR + jq, dead, tol2
+              nrot += pair_reg<NPL, FULL>(u, Q + (size_t)jq * N, N, lane, aP, s_nrm2 + q * BR + jq, dead, tol2, small2
 #ifdef TCB_TIMING
                                           , tacc
 #endif
