@@ -488,7 +488,7 @@ __global__ void __launch_bounds__(NT) jacobi_rows_cluster_kernel(TcDev d, LayerA
   const int rank = (int)cluster_rank();
   const int gw = rank * NW + warp, nw = CS * NW;  // this warp among the warps of the cluster
   const double tol = 2.0 * sqrt((double)N) * 2.220446049250313e-16;
-  const double tol2 = tol * tol;
+  const double tol2_final = tol * tol;
   double dead = 0.0;
   int sweep = 0;
   for (; sweep < MAX_SWEEPS; ++sweep) {
@@ -506,6 +506,10 @@ __global__ void __launch_bounds__(NT) jacobi_rows_cluster_kernel(TcDev d, LayerA
       for (int r = tid; r < M; r += NT) p += __ldcg(nrm2 + r);
       dead = DEAD_REL2 * block_sum(p, red);
     }
+    // threshold sweeps and their stopping rule as in tc_jacobi_blocked.cuh (here a skipped rotation also saves the
+    // write-back of the two rows, half of the L2 traffic of the pair)
+    const double tol2 = sweep < 4 ? fmax(tol2_final, d.thr_sched[sweep]) : tol2_final;
+    const double small2 = tol2 > tol2_final ? tol2_final : SMALL_REL2;
     int nrot = 0;
     for (int r = 0; r < M - 1; ++r) {
       for (int k = gw; k < M / 2; k += nw) {
@@ -535,8 +539,8 @@ __global__ void __launch_bounds__(NT) jacobi_rows_cluster_kernel(TcDev d, LayerA
         double gr = warp_sum(g0 + g1);
         double gi = warp_sum(h0 + h1);
         const double g2 = gr * gr + gi * gi;
+        nrot += g2 > small2 * ai * aj;
         if (!(g2 > tol2 * ai * aj)) continue;
-        nrot += g2 > SMALL_REL2 * ai * aj;
         const double ga = sqrt(g2);
         const double zeta = (aj - ai) / (2.0 * ga);
         const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
