@@ -189,7 +189,7 @@ __device__ __forceinline__ int pair_smem(cplx *xi, cplx *xj, int N, int lane, do
     *ni = r.ni;
     *nj = r.nj;
   }
-  return big;
+  return big | (1 << 16);  // bits 0..15 count the pairs that keep the iteration going, bits 16.. the rotations made
 }
 
 // row i in registers (u, its squared norm ai too), row j in shared memory.  The row is loaded before anything is
@@ -241,7 +241,7 @@ __device__ __forceinline__ int pair_reg(cplx (&u)[NPL], cplx *xj, int N, int lan
 #ifdef TCB_TIMING
   tacc[5] += 1;
 #endif
-  return big;
+  return big | (1 << 16);
 }
 
 template <int NPL, bool FULL>
@@ -265,6 +265,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
   const int nblk = (K + BR - 1) / BR;
   const double tol = 2.0 * sqrt((double)N) * 2.220446049250313e-16;
   const double tol2_final = tol * tol;
+  bool thr_off = false;
   const uint32_t row_bytes = (uint32_t)N * sizeof(cplx);
   uint32_t phP = 0, phQ0 = 0, phQ1 = 0;  // scalars, not arrays: dynamic indexing would put them in local memory
   int verBase0 = 0, verBase1 = 0;
@@ -294,7 +295,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
     // 1e-2, 1e-3, 1e-4, 1e-6 in sweeps 0..3); a small rotation made now is undone by the large ones around it and has
     // to be made again.  Same final accuracy and sweep count, a fifth fewer rotations (NumPy model on TEBD matrices).
     // The parameter of the pair functions called tol2 is this sweep's rotation threshold from here on.
-    const double tol2 = sweep < 4 ? fmax(tol2_final, d.thr_sched[sweep]) : tol2_final;
+    const double tol2 = (sweep < 4 && !thr_off) ? fmax(tol2_final, d.thr_sched[sweep]) : tol2_final;
     // stopping rule: a sweep that rotated every pair above the final tolerance and found them all below 1e-8 ends the
     // iteration (quadratic convergence: what is left is below 1e-16); a threshold sweep has skipped pairs, so there
     // anything above the final tolerance keeps the iteration going
@@ -463,9 +464,13 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
     }
     if (lane == 0 && nrot) atomicAdd(s_rot, nrot);
     __syncthreads();
-    const int tot = __reduce_max_sync(0xffffffffu, *s_rot);
+    const int both = __reduce_max_sync(0xffffffffu, *s_rot);
+    const int tot = both & 0xffff;
     __syncthreads();
     if (tot == 0) break;
+    // a threshold sweep that found nothing to rotate (a nearly orthogonal matrix: weak gates, small chi) would be
+    // followed by more of the same: go straight to the final tolerance
+    if (((unsigned)both >> 16) == 0) thr_off = true;
   }
 #ifdef TCB_TIMING
   if (K == 256 && N == 256 && warp == 3 && lane == 0) {
