@@ -326,7 +326,7 @@ def run_ours(a):
                 'frac': (achieved / fp64_peak) if achieved else None,
                 'traffic': ncu_traffic_gb(),
                 'traffic_unit': 'GB per Jacobi launch (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full capture '
-                                'of a 32-chain layer, profiles/r01d_ncu_kernels.txt); algorithmic: 0.8 GB',
+                                'of a 32-chain layer, profiles/r01e_ncu_kernels.txt); algorithmic: 0.8 GB',
                 'peak_source': 'tc_probe_fp64 (DFMA chain, all SMs) measured in this run; MEASURED_PEAKS.json has no '
                                f'FP64 entry (hbm_gbs={peaks.get("hbm_gbs")}); DMMA probe {dmma_peak:.1f} TFLOP/s',
                 'flops_model': 'SURVEY 8d: 4(4m^2 n + 8 m n^2 + 9 n^3) per update, summed over the actual bond '
