@@ -495,33 +495,44 @@ static int run_periods(tc_ctx *c, int n) {
   if (!c->gfork) CK(cudaEventCreateWithFlags(&c->gfork, cudaEventDisableTiming));
   CK(cudaEventRecord(c->gfork, c->stream));
   const int wpg = d.ws_chains / G;
-  for (int g = 0; g < G; ++g) {
-    const int r_lo = (int)((long long)d.R * g / G), r_hi = (int)((long long)d.R * (g + 1) / G);
-    CK(cudaStreamWaitEvent(c->gstreams[g], c->gfork, 0));
-    for (int t = 0; t < n; ++t)
+  for (int g = 0; g < G; ++g) CK(cudaStreamWaitEvent(c->gstreams[g], c->gfork, 0));
+  // period-major enqueue order: a stream takes only so many pending launches before the host blocks; feeding one
+  // group all its periods first would let that group run alone for long calls
+  for (int t = 0; t < n; ++t)
+    for (int g = 0; g < G; ++g) {
+      const int r_lo = (int)((long long)d.R * g / G), r_hi = (int)((long long)d.R * (g + 1) / G);
       if (run_period_on(c, r_lo, r_hi, c->gstreams[g], g * wpg, wpg)) return 1;
+    }
+  for (int g = 0; g < G; ++g) {
     CK(cudaEventRecord(c->gjoin[g], c->gstreams[g]));
+    CK(cudaStreamWaitEvent(c->stream, c->gjoin[g], 0));
   }
-  for (int g = 0; g < G; ++g) CK(cudaStreamWaitEvent(c->stream, c->gjoin[g], 0));
   return 0;
 }
 
-static int measure_into(tc_ctx *c, double *rdm, double *Z, double *ent, double *ov, int32_t *chi) {
+// observables of the chains [r_lo, r_hi) on stream st; the output arrays are indexed by the absolute chain number
+static int measure_range(tc_ctx *c, double *rdm, double *Z, double *ent, double *ov, int32_t *chi, int r_lo, int r_hi,
+                         cudaStream_t st) {
   const TcDev &d = c->d;
-  ProfScope ps(c, TC_PROF_MEASURE);
+  const int nr = r_hi - r_lo;
+  if (nr <= 0) return 0;
   if (rdm || Z || ent) {
-    tco::measure_kernel<<<dim3(d.L, d.R), tco::NT, 0, c->stream>>>(d, rdm, Z, ent);
+    tco::measure_kernel<<<dim3(d.L, nr), tco::NT, 0, st>>>(d, r_lo, rdm, Z, ent);
     LAUNCHED();
   }
   if (ov) {
-    tco::overlap_product_kernel<<<d.R, tco::NT, (2 * d.chi_cap + (tco::NT / 32) * tco::OVC) * sizeof(cplx), c->stream>>>(d, ov);
+    tco::overlap_product_kernel<<<nr, tco::NT, (2 * d.chi_cap + (tco::NT / 32) * tco::OVC) * sizeof(cplx), st>>>(d, r_lo, ov);
     LAUNCHED();
   }
   if (chi) {
-    tco::chi_record_kernel<<<64, 256, 0, c->stream>>>(d, chi);
+    tco::chi_record_kernel<<<64, 256, 0, st>>>(d, r_lo, nr, chi);
     LAUNCHED();
   }
   return 0;
+}
+static int measure_into(tc_ctx *c, double *rdm, double *Z, double *ent, double *ov, int32_t *chi) {
+  ProfScope ps(c, TC_PROF_MEASURE);
+  return measure_range(c, rdm, Z, ent, ov, chi, 0, c->d.R, c->stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1006,7 +1017,7 @@ int tc_floquet_run_dev(tc_ctx *c, int n_steps, int measure_every, int rec0, int 
     ++k;
   }
   // periods t = 0 .. n_steps-1, a record after every period with t % measure_every == 0; the periods between two
-  // records go to run_periods in one call (the chain groups only join where a record needs every chain)
+  // records go to run_periods in one call and the chain groups join where a record needs every chain
   int t = 0;
   while (t < n_steps) {
     const int tn = (t + measure_every - 1) / measure_every * measure_every;  // next recorded period

@@ -52,8 +52,8 @@ __global__ void one_site_kernel(TcDev d, int r0, int site0, const cplx *op_fixed
 // one CTA per (site, chain): single-site reduced density matrix, <Z>, and the entropy of the bond
 // to the right of the site.  rdm[R][L][4] = (rho00, rho11, Re rho01, Im rho01), rho_pq = <p|rho|q>.
 // Output rows are indexed by the chain's position in the launch (r - r0) plus out_r0.
-__global__ void __launch_bounds__(NT) measure_kernel(TcDev d, double *rdm, double *Z, double *ent) {
-  const int site = blockIdx.x, r = blockIdx.y;
+__global__ void __launch_bounds__(NT) measure_kernel(TcDev d, int r0, double *rdm, double *Z, double *ent) {
+  const int site = blockIdx.x, r = r0 + blockIdx.y;  // grid (L, chains of this launch), chains r0 ..
   const int *c = d.chi + (size_t)r * (d.L + 1);
   const int chiL = c[site], chiR = c[site + 1];
   const cplx *B = site_ptr(d, r, site);
@@ -106,8 +106,8 @@ __global__ void __launch_bounds__(NT) measure_kernel(TcDev d, double *rdm, doubl
 // per thread: 0.50 ms per snapshot at the metric shape.)
 // dynamic smem: (2 chi_cap + 8 OVC) cplx
 constexpr int OVC = 128;  // columns per pass
-__global__ void __launch_bounds__(NT) overlap_product_kernel(TcDev d, double *ov) {
-  const int r = blockIdx.x;
+__global__ void __launch_bounds__(NT) overlap_product_kernel(TcDev d, int r0, double *ov) {
+  const int r = r0 + blockIdx.x;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx *v = reinterpret_cast<cplx *>(smem_raw);
   cplx *vn = v + d.chi_cap;
@@ -156,10 +156,11 @@ __global__ void __launch_bounds__(NT) overlap_product_kernel(TcDev d, double *ov
   }
 }
 
-__global__ void chi_record_kernel(TcDev d, int32_t *out) {
-  const size_t n = (size_t)d.R * (d.L + 1);
+// chains r0 .. r0 + nr - 1
+__global__ void chi_record_kernel(TcDev d, int r0, int nr, int32_t *out) {
+  const size_t lo = (size_t)r0 * (d.L + 1), n = (size_t)nr * (d.L + 1);
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x)
-    out[e] = d.chi[e];
+    out[lo + e] = d.chi[lo + e];
 }
 
 // General transfer-matrix contraction between chain ra of context da (bra, conjugated) and chain rb
