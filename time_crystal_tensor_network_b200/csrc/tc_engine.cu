@@ -494,6 +494,10 @@ static int run_periods(tc_ctx *c, int n) {
   }
   if (!c->gfork) CK(cudaEventCreateWithFlags(&c->gfork, cudaEventDisableTiming));
   CK(cudaEventRecord(c->gfork, c->stream));
+  // workspace slots of group g: its own chains when the workspace holds every chain (the usual case; an even split
+  // would leave the larger groups of an uneven partition one slot short and make them run a second, almost empty
+  // chunk per layer), an even share otherwise
+  const bool whole = d.ws_chains >= d.R;
   const int wpg = d.ws_chains / G;
   for (int g = 0; g < G; ++g) CK(cudaStreamWaitEvent(c->gstreams[g], c->gfork, 0));
   // period-major enqueue order: a stream takes only so many pending launches before the host blocks; feeding one
@@ -501,7 +505,7 @@ static int run_periods(tc_ctx *c, int n) {
   for (int t = 0; t < n; ++t)
     for (int g = 0; g < G; ++g) {
       const int r_lo = (int)((long long)d.R * g / G), r_hi = (int)((long long)d.R * (g + 1) / G);
-      if (run_period_on(c, r_lo, r_hi, c->gstreams[g], g * wpg, wpg)) return 1;
+      if (run_period_on(c, r_lo, r_hi, c->gstreams[g], whole ? r_lo : g * wpg, whole ? r_hi - r_lo : wpg)) return 1;
     }
   for (int g = 0; g < G; ++g) {
     CK(cudaEventRecord(c->gjoin[g], c->gstreams[g]));
