@@ -65,6 +65,7 @@ struct tc_ctx {
   bool have_model = false;
   bool blocked_attr_set = false;
   bool rb_attr_set = false;
+  bool no_small_kernel = false;  // TC_SMALL_KERNEL=0: the 128-register Jacobi kernel for narrow contexts too (A/B)
   bool qrw_attr_set = false;
   int jacobi_kind = 1;  // TC_JACOBI = blocked (1, default: 16-warp kernel) | rb (2: register-blocked, experimental) | simple (0)
   bool force_simple_jacobi = false;  // TC_JACOBI=simple: the warp-per-pair kernel for every size (A/B testing)
@@ -394,10 +395,14 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
       } else if (d.n2 <= tcb::MAX_N && !c->force_simple_jacobi) {
         const size_t smem = (size_t)3 * tcb::BR * d.n2 * sizeof(cplx) + d.n2 * sizeof(double) + 64 + 2 * tcb::BR * sizeof(int);
         if (!c->blocked_attr_set) {
-          CK(cudaFuncSetAttribute(tcb::jacobi_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          CK(cudaFuncSetAttribute(tcb::jacobi_blocked_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          CK(cudaFuncSetAttribute(tcb::jacobi_blocked_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           c->blocked_attr_set = true;
         }
-        tcb::jacobi_blocked_kernel<<<dim3(nr, nb), tcb::NT, smem, st>>>(d, a);
+        if (d.n2 <= 128 && !c->no_small_kernel)
+          tcb::jacobi_blocked_kernel<4><<<dim3(nr, nb), tcb::NT, smem, st>>>(d, a);
+        else
+          tcb::jacobi_blocked_kernel<8><<<dim3(nr, nb), tcb::NT, smem, st>>>(d, a);
       } else {
         // wide matrices: a cluster of CS CTAs per matrix when the launch has too few matrices to fill the GPU
         int CS = 1;
@@ -585,6 +590,7 @@ int tc_ctx_create(int device, int L, int chi_cap, int R, void *arena, size_t are
   }
   c->arena_bytes = lo.total;
   c->ngroups = 4;
+  if (const char *e = getenv("TC_SMALL_KERNEL")) c->no_small_kernel = atoi(e) == 0;
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
   if (const char *e = getenv("TC_WIDE_CLUSTER")) c->wide_cluster = atoi(e);
   if (const char *e = getenv("TC_GROUPS")) c->ngroups = atoi(e) > 0 ? atoi(e) : 1;

@@ -498,8 +498,12 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
   }
 }
 
-// dynamic smem: 3 * BR * n2 cplx (P, Q0, Q1) + n2 doubles + 3 mbarriers (n2 <= MAX_N)
-__global__ void __launch_bounds__(NT, CTAS_PER_SM) jacobi_blocked_kernel(TcDev d, LayerArgs a) {
+// dynamic smem: 3 * BR * n2 cplx (P, Q0, Q1) + n2 doubles + 3 mbarriers (n2 <= MAX_N).
+// MAXNPL = 8: any matrix up to 256 columns, one CTA per SM (128 registers).  MAXNPL = 4: contexts whose widest matrix
+// has 128 columns (chi_cap <= 64: BASELINE configs 2 and 3) -- rows are half as long, 64 registers and 98 KB of shared
+// memory are enough, and two CTAs per SM hide each other's latency chains.
+template <int MAXNPL>
+__global__ void __launch_bounds__(NT, MAXNPL <= 4 ? 2 * CTAS_PER_SM : CTAS_PER_SM) jacobi_blocked_kernel(TcDev d, LayerArgs a) {
   Bond b;
   // blockIdx.x = chain, blockIdx.y = rank of the bond in centre-out order (largest matrices first)
   if (!get_bond(d, a, centre_out(blockIdx.y, a.nb), blockIdx.x, b)) return;
@@ -521,15 +525,17 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) jacobi_blocked_kernel(TcDev d
   if (threadIdx.x < 2 * BR) reinterpret_cast<int *>(bars + 4)[threadIdx.x] = 0;
   __syncthreads();
   const int npl = (N + 31) / 32;
-  if (N == 256)
+  if (MAXNPL >= 8 && N == 256)
     sweeps<8, true>(d, b, X, K, N, &s_rot, red);
   else if (npl <= 1)
     sweeps<1, false>(d, b, X, K, N, &s_rot, red);
   else if (npl <= 2)
     sweeps<2, false>(d, b, X, K, N, &s_rot, red);
+  else if (MAXNPL <= 4 && N == 128)
+    sweeps<4, true>(d, b, X, K, N, &s_rot, red);
   else if (npl <= 4)
     sweeps<4, false>(d, b, X, K, N, &s_rot, red);
-  else
+  else if (MAXNPL >= 8)
     sweeps<8, false>(d, b, X, K, N, &s_rot, red);
 }
 }  // namespace tcb
