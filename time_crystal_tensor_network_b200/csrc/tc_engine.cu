@@ -473,20 +473,28 @@ static int run_period_on(tc_ctx *c, int r_lo, int r_hi, cudaStream_t st, int ws_
 // n Floquet periods of every chain.  With G > 1 chain groups each group runs all its n periods on its own stream
 // (fork after what is already queued on the context's stream, join before what comes next); per-kernel profiling
 // needs the launches in one stream and runs the groups one after the other.
-static int run_periods(tc_ctx *c, int n) {
+// after(t, r_lo, r_hi, st) is called once per period t and chain range, on the stream that ran that range: the records
+// of tc_floquet_run_dev are taken there, group by group, so that a record does not make the groups wait for each
+// other (a join per period costs 2 % at the metric shape: the slowest group's last layer runs alone).
+template <class After>
+static int run_periods_with(tc_ctx *c, int n, After &&after) {
   const TcDev &d = c->d;
   if (n <= 0) return 0;
   if (d.L < 2) {
-    for (int t = 0; t < n; ++t)
+    for (int t = 0; t < n; ++t) {
       if (run_kick_all(c)) return 1;
+      if (after(t, 0, d.R, c->stream)) return 1;
+    }
     return 0;
   }
   int G = c->ngroups;
   if (G > d.R) G = d.R;
   if (G > d.ws_chains) G = d.ws_chains;
   if (c->profile || G <= 1) {
-    for (int t = 0; t < n; ++t)
+    for (int t = 0; t < n; ++t) {
       if (run_period_on(c, 0, d.R, c->stream, 0, d.ws_chains)) return 1;
+      if (after(t, 0, d.R, c->stream)) return 1;
+    }
     return 0;
   }
   while ((int)c->gstreams.size() < G) {
@@ -511,12 +519,16 @@ static int run_periods(tc_ctx *c, int n) {
     for (int g = 0; g < G; ++g) {
       const int r_lo = (int)((long long)d.R * g / G), r_hi = (int)((long long)d.R * (g + 1) / G);
       if (run_period_on(c, r_lo, r_hi, c->gstreams[g], whole ? r_lo : g * wpg, whole ? r_hi - r_lo : wpg)) return 1;
+      if (after(t, r_lo, r_hi, c->gstreams[g])) return 1;
     }
   for (int g = 0; g < G; ++g) {
     CK(cudaEventRecord(c->gjoin[g], c->gstreams[g]));
     CK(cudaStreamWaitEvent(c->stream, c->gjoin[g], 0));
   }
   return 0;
+}
+static int run_periods(tc_ctx *c, int n) {
+  return run_periods_with(c, n, [](int, int, int, cudaStream_t) { return 0; });
 }
 
 // observables of the chains [r_lo, r_hi) on stream st; the output arrays are indexed by the absolute chain number
@@ -1026,18 +1038,16 @@ int tc_floquet_run_dev(tc_ctx *c, int n_steps, int measure_every, int rec0, int 
     if (rec(k)) return 1;
     ++k;
   }
-  // periods t = 0 .. n_steps-1, a record after every period with t % measure_every == 0; the periods between two
-  // records go to run_periods in one call and the chain groups join where a record needs every chain
-  int t = 0;
-  while (t < n_steps) {
-    const int tn = (t + measure_every - 1) / measure_every * measure_every;  // next recorded period
-    if (tn >= n_steps) return run_periods(c, n_steps - t);
-    if (run_periods(c, tn - t + 1)) return 1;
-    if (rec(k)) return 1;
-    ++k;
-    t = tn + 1;
-  }
-  return 0;
+  // periods t = 0 .. n_steps-1, a record after every period with t % measure_every == 0, taken chain range by chain
+  // range on the stream that ran the range (see run_periods_with); the call joins the groups once, at its end
+  const int k0 = k;
+  return run_periods_with(c, n_steps, [&](int t, int r_lo, int r_hi, cudaStream_t st) {
+    if (t % measure_every) return 0;
+    const int kk = k0 + t / measure_every;
+    ProfScope ps(c, TC_PROF_MEASURE);  // profile mode runs everything on the context's stream
+    return measure_range(c, nullptr, Z_dev ? Z_dev + zs * kk : nullptr, (ent_dev && es) ? ent_dev + es * kk : nullptr,
+                         ov_dev ? ov_dev + os * kk : nullptr, chi_dev ? chi_dev + cs * kk : nullptr, r_lo, r_hi, st);
+  });
 }
 
 int tc_floquet_run_host(tc_ctx *c, const double *gates_host, const double *kick_host, int n_steps, int measure_every,
