@@ -122,8 +122,11 @@ int tc_correlation(tc_ctx *ctx, int r, int i, int j, const double *op1_host, con
      ent_dev[n_rec][R][L-1]  bond entropies
      ov_dev [n_rec][R][2]    <psi_0|psi(t)> with psi_0 the product state given to tc_set_product_state
      chi_dev[n_rec][R][L+1]  int32 bond dimensions
-   If measure_t0 != 0 record rec0-1... is not written; call with n_steps = 0, measure_t0 = 1 to
-   record the current state into record rec0.                                                      */
+   If measure_now != 0 the current state is recorded first, into record rec0, and the records of
+   the periods follow from rec0 + 1 (n_steps = 0, measure_now = 1 records the current state only).
+   Asynchronous: the chain groups take their records on their own streams and are joined to the
+   context's stream when the call returns, so work enqueued on that stream afterwards (and the
+   host after tc_sync) sees every record.                                                          */
 int tc_floquet_run_dev(tc_ctx *ctx, int n_steps, int measure_every, int rec0, int measure_now,
                        double *Z_dev, double *ent_dev, double *ov_dev, int32_t *chi_dev);
 /* same with HOST buffers for inputs and outputs (the call the end-to-end benchmark times): uploads
