@@ -29,11 +29,14 @@ def subharmonic_bin(series):
 def run_ensemble(tag, L, chi, hs, eps, n_periods, measure_every=1, **kw):
     t0 = time.time()
     ens = eng.FloquetEnsemble(L, 1.0, 1.0, hs, epsilon=eps, chi_max=chi, mode='tebd', svd_min=1e-12, trunc_cut=1e-7, **kw)
+    t1 = time.time()
     out = ens.run(n_periods, measure_every=measure_every)
     dt = time.time() - t0
+    run_s = time.time() - t1
     R = hs.shape[0]
     stag = (out['Z'] * ((-1.0) ** np.arange(L))).mean(axis=2)          # [T][R] staggered magnetisation
     res = {'config': tag, 'L': L, 'chi_max': chi, 'chains': R, 'periods': n_periods, 'wall_s': round(dt, 2),
+           'setup_s': round(t1 - t0, 2), 'run_s': round(run_s, 3),   # setup: context, arena, model upload (the first one also CUDA start-up)
            'chain_steps_per_s': round(R * n_periods / dt, 1), 'chi_reached': int(out['chi'].max()),
            'S_mid_final_mean': float(out['S_ent'][-1][:, L // 2 - 1].mean()),
            'LE_final_mean': float(out['LE'][-1].mean()), 'flags': {k: float(v) for k, v in out['flags'].items()}}
@@ -56,6 +59,9 @@ if 1 in WHICH:
                                           np.allclose(np.abs(stag[:, 0]), 1.0, atol=1e-12))
     res['subharmonic_bin,half_drive_bin'] = subharmonic_bin(stag[:, 0])
     emit(res)
+    # the same once more: the first line carries the process's CUDA start-up and module load
+    res2, _, _ = run_ensemble('1: perfect time crystal (second run in the process)', 10, 32, np.zeros((1, 10)), 0.0, 100)
+    emit(res2)
 if 2 in WHICH:
     L, R, n = 20, 256, (40 if QUICK else 200)
     hs = np.array([eng.disorder_fields(L, 0.3, 1000 + r) for r in range(R)])
