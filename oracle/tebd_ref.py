@@ -420,3 +420,31 @@ def run(n_sites, J, h_fields, tau, n_periods, epsilon=0.0, state='neel', up_inde
     return dict(Z=np.array(Z), S_ent=np.array(Sent), LE=np.array(LE),
                 chi=np.array(chi, dtype=int).reshape(len(chi), -1), times=np.array(times),
                 trunc_err=terr, psi=psi)
+
+
+def run_schedule(n_sites, J, h_fields, tau, schedule, state='neel', up_index=1, mode='tebd', trunc=None):
+    """`run` with a piecewise-constant kick imperfection: schedule = [(epsilon, n_periods), ...] (bench.py's
+    two-phase workload: entangle at a large epsilon until the bonds saturate, then evolve at the target epsilon).
+    A record before the first period and after every period; the Ising gates do not depend on epsilon."""
+    _, gates = make_gates(n_sites, J, h_fields, tau, 0.0)
+    psi0 = product_state(n_sites, state, up_index)
+    psi = psi0.copy()
+    Z, Sent, LE, chi, eps_t = [], [], [], [], []
+    terr = 0.0
+
+    def measure():
+        Z.append(site_z(psi))
+        Sent.append(psi.entanglement_entropy())
+        LE.append(abs(psi0.overlap(psi)) ** 2)
+        chi.append(list(psi.chi))
+
+    measure()
+    for eps, n in schedule:
+        kick, _ = make_gates(2, J, np.zeros(2), tau, eps)
+        for _ in range(n):
+            psi, e = floquet_step(psi, kick, gates, mode=mode, trunc=trunc)
+            terr += e
+            eps_t.append(eps)
+            measure()
+    return dict(Z=np.array(Z), S_ent=np.array(Sent), LE=np.array(LE),
+                chi=np.array(chi, dtype=int).reshape(len(chi), -1), eps=np.array(eps_t), trunc_err=terr, psi=psi)

@@ -25,9 +25,9 @@
 // (`uni`) and spin loops exit on a vote, otherwise every later shuffle carries a BRA.DIV divergence check; rsqrt(double)
 // hides a branch, `rsqrt_nb` does not.
 #pragma once
-#include "tc_common.cuh"
-#include "tc_jacobi.cuh"
-#include "tc_jacobi_blocked.cuh"
+#include "../../time_crystal_tensor_network_b200/csrc/tc_common.cuh"
+#include "../../time_crystal_tensor_network_b200/csrc/tc_jacobi.cuh"
+#include "../../time_crystal_tensor_network_b200/csrc/tc_jacobi_blocked.cuh"
 
 namespace tcr {
 using tcb::bulk_load;

@@ -7,7 +7,7 @@
 // usage: pair_chain <warps per CTA>; prints cycles per dual step (= 2 row pairs) per warp and FP64 pipe share
 #include <cstdio>
 #include <cstdlib>
-#include "../../time_crystal_tensor_network_b200/csrc/tc_jacobi_rb.cuh"
+#include "../experiments/tc_jacobi_rb.cuh"
 using namespace tcr;
 // primitives of the software-pipelined visit that was measured and dropped (see tc_jacobi_rb.cuh header)
 struct RotP {

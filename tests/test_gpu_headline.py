@@ -1,0 +1,180 @@
+"""Parity of the CUDA path against the LAPACK TEBD oracle at the sizes the benchmark and the BASELINE configurations
+are quoted on (north star: <Z_i>(t), bond entropies, Loschmidt echo <= 1e-8 absolute at equal chi_max and truncation
+cut-offs; spectral peak positions exactly).
+
+The oracle (oracle/tebd_ref.py, update_bond_tebd + truncate(): /root/reference/src/models/kicked_ising.py:100-126,162-188
+on TeNPy's TEBD update) needs tens of seconds per chain at these sizes, so its records are committed as fixtures
+(tests/golden/headline_*.npz etc., written by oracle/make_headline_golden.py) and re-computed live with TC_GOLDEN_LIVE=1.
+
+Every comparison goes through the C ABI (FloquetEnsemble -> tc_floquet_run_host).
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import tebd_ref  # noqa: E402  (checker only)
+from oracle.make_headline_golden import CASES  # noqa: E402
+
+TOL = 1e-8
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _oracle(name):
+    """{key_k: array} of the oracle for every seed of the case: the committed fixture, or a live run."""
+    c = CASES[name]
+    if os.environ.get('TC_GOLDEN_LIVE') == '1':
+        out = {}
+        for k, seed in enumerate(c['seeds']):
+            h = tebd_ref.disorder_fields(c['L'], c['W'], seed)
+            r = tebd_ref.run_schedule(c['L'], 1.0, h, 1.0, c['schedule'], mode='tebd', trunc=c['trunc'])
+            for key in ('Z', 'S_ent', 'LE', 'chi'):
+                out[f'{key}_{k}'] = r[key]
+            out[f'h_{k}'] = h
+        return out
+    return dict(np.load(os.path.join(ROOT, 'tests', 'golden', name + '.npz')))
+
+
+def _gpu_schedule(name, env=None):
+    """The case's chains in one context, the kick imperfection switched between the phases of the schedule (the Ising
+    gates do not depend on it): records before the first period and after every period."""
+    from time_crystal_tensor_network_b200 import engine as eng
+    c = CASES[name]
+    L = c['L']
+    hs = np.array([eng.disorder_fields(L, c['W'], s) for s in c['seeds']])
+    ens = eng.FloquetEnsemble(L, 1.0, 1.0, hs, epsilon=c['schedule'][0][0], mode='tebd', state='neel', **c['trunc'])
+    parts = []
+    for eps, n in c['schedule']:
+        kick = np.ascontiguousarray(np.broadcast_to(eng.kick_matrix(eps), (len(hs), 2, 2)))
+        ens.ctx.set_model(ens.gates, kick)
+        parts.append(ens.run(n))
+    out = {k: np.concatenate([p[k] for p in parts], axis=0) for k in ('Z', 'S_ent', 'LE', 'chi')}
+    out['flags'] = parts[-1]['flags']
+    out['hs'] = hs
+    ens.close()
+    return out
+
+
+def _compare(name, out, ref, tol=TOL):
+    c = CASES[name]
+    worst = {}
+    for k in range(len(c['seeds'])):
+        assert np.array_equal(out['hs'][k], ref[f'h_{k}'])
+        chi_ref = ref[f'chi_{k}']
+        assert np.array_equal(out['chi'][:, k, 1:-1], chi_ref), \
+            f'{name} chain {k}: bond-dimension tables differ first at record ' \
+            f'{int(np.argmax(np.any(out["chi"][:, k, 1:-1] != chi_ref, axis=1)))}'
+        for key in ('Z', 'S_ent', 'LE'):
+            dev = np.abs(out[key][:, k] - ref[f'{key}_{k}'])
+            per_t = dev.reshape(dev.shape[0], -1).max(axis=1)
+            worst[(key, k)] = per_t
+    msg = '; '.join(f'{key}[{k}] max {v.max():.2e} at record {int(v.argmax())}' for (key, k), v in worst.items())
+    print(f'{name}: {msg}')
+    for (key, k), v in worst.items():
+        assert v.max() < tol, f'{name}: {msg}'
+    assert out['flags']['svd_not_converged'] == 0 and out['flags']['chi_cap_overflow'] == 0
+
+
+def test_headline_shape_against_oracle(engine):
+    """bench.py's workload: L = 32, chi_max = 128, svd_min 1e-12, trunc_cut 1e-7, two chains (seeds 1000, 1001), nine
+    periods at eps = 0.3 (the central bonds reach chi_max in period 8: theta = 256 x 256 with the chi_max cut
+    active, the `sweeps<8, true>` instance of the blocked Jacobi kernel) and three periods at eps = 0.1."""
+    name = 'headline_L32_chi128'
+    out = _gpu_schedule(name)
+    assert out['chi'].max() == 128 and out['chi'][-1, :, 16].min() == 128
+    _compare(name, out, _oracle(name))
+
+
+def test_wide_matrices_truncated_against_oracle(engine):
+    """chi_max = 256 binding (theta 512 x 512: the wide QR instance and the cluster Jacobi kernel, BASELINE config 4's
+    regime) at L = 18, where an untruncated bond would reach 512."""
+    name = 'wide_L18_chi256'
+    out = _gpu_schedule(name)
+    assert out['chi'].max() == 256
+    _compare(name, out, _oracle(name))
+
+
+def test_phase_diagram_point_shape_against_oracle(engine):
+    """BASELINE config 3's grid point: L = 24, chi_max = 64, 20 periods at eps = 0.1 (the two-CTA-per-SM narrow
+    instance of the Jacobi kernel)."""
+    name = 'c3_L24_chi64'
+    out = _gpu_schedule(name)
+    _compare(name, out, _oracle(name))
+
+
+def test_subharmonic_peak_position_of_an_entangling_run(engine):
+    """Period-doubling spectral peak positions exactly: 64 periods at eps = 0.1 (bond dimension up to 32, truncation
+    active); the FFT bin of the largest positive-frequency component of the staggered magnetisation and of the
+    Loschmidt echo are the oracle's, and the reference's own extractors (src/core/observables.py:153-221,372-439,
+    main.calculate_fourier_spectrum) return the same numbers on both series."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import main as m
+    from time_crystal_tensor_network_b200.core import observables as obs
+    name = 'dtc_L12_chi32'
+    c = CASES[name]
+    out = _gpu_schedule(name)
+    ref = _oracle(name)
+    _compare(name, out, ref)
+    L, T = c['L'], 2.0
+    sign = (-1.0) ** np.arange(L)
+    times = np.arange(out['Z'].shape[0]) * T
+    for k in range(len(c['seeds'])):
+        stag = (out['Z'][:, k] * sign).mean(axis=1)
+        stag_ref = (ref[f'Z_{k}'] * sign).mean(axis=1)
+
+        def peak_bin(series):
+            w = (series - series.mean()) * np.hanning(len(series))
+            f = np.fft.fft(w)
+            fr = np.fft.fftfreq(len(w), d=T)
+            pos = np.nonzero(fr > 0)[0]
+            return int(pos[np.argmax(np.abs(f[pos]))]), fr
+
+        b, fr = peak_bin(stag)
+        b_ref, _ = peak_bin(stag_ref)
+        assert b == b_ref
+        assert abs(fr[b] - 0.5 / T) <= 1.01 / (len(times) * T)           # the sub-harmonic bin (half the drive frequency)
+        b_le, _ = peak_bin(out['LE'][:, k])
+        b_le_ref, _ = peak_bin(ref[f'LE_{k}'])
+        assert b_le == b_le_ref
+        a = obs.extract_subharmonic_amplitude(times, stag, T)
+        a_ref = obs.extract_subharmonic_amplitude(times, stag_ref, T)
+        assert abs(a - a_ref) < TOL
+        f1, p1 = m.calculate_fourier_spectrum(times, stag, T)
+        f2, p2 = m.calculate_fourier_spectrum(times, stag_ref, T)
+        assert int(np.argmax(p1)) == int(np.argmax(p2)) and np.array_equal(f1, f2)
+        assert abs(obs.extract_subharmonic_amplitude_from_loschmidt(times, out['LE'][:, k], T) -
+                   obs.extract_subharmonic_amplitude_from_loschmidt(times, ref[f'LE_{k}'], T)) < 1e-6
+
+
+@pytest.mark.parametrize('switch', ['TC_THRESH=0', 'TC_EARLY_STOP=0'])
+def test_svd_shortcuts_change_nothing_at_rounding_level(engine, switch, monkeypatch):
+    """The pattern DESIGN.md prescribes for every shortcut inside the SVD: same saturated state (256 x 256 theta with
+    the chi_max cut active), one more period with the shortcut on and off, agreement at rounding level (1e-12), far
+    below what the 1e-8 oracle comparisons could see.  Shortcuts: threshold sweeps (TC_THRESH=0 rotates every pair in
+    every sweep), the quadratic-convergence stopping rule (TC_EARLY_STOP=0 runs the verification sweep)."""
+    from time_crystal_tensor_network_b200 import engine as eng
+    L, chi = 32, 128
+    hs = np.array([eng.disorder_fields(L, 0.3, 1000)])
+    kw = dict(epsilon=0.3, chi_max=chi, mode='tebd', svd_min=1e-12, trunc_cut=1e-7)
+    base = eng.FloquetEnsemble(L, 1.0, 1.0, hs, **kw)
+    base.run(9)
+    assert base.ctx.chi()[0, L // 2] == chi
+    key, val = switch.split('=')
+    monkeypatch.setenv(key, val)
+    other = eng.FloquetEnsemble(L, 1.0, 1.0, hs, **kw)       # the switch is read when a context is created
+    monkeypatch.delenv(key)
+    other.ctx._arena.copy_(base.ctx._arena)
+    a = base.run(1, measure_now=False)
+    b = other.run(1, measure_now=False)
+    assert np.array_equal(a['chi'], b['chi'])
+    for k in ('Z', 'S_ent', 'LE'):
+        assert np.max(np.abs(a[k] - b[k])) < 1e-12, k
+    # the kept Schmidt values themselves, relative
+    for bond in (L // 2 - 1, L // 2, L // 2 + 1):
+        sa, sb = base.ctx.get_S(0, bond), other.ctx.get_S(0, bond)
+        assert np.max(np.abs(sa - sb) / sa) < 1e-10
+    base.close()
+    other.close()

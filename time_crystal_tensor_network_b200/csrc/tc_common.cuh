@@ -59,6 +59,8 @@ struct TcDev {
   int rot64;          // TC_ROT64 A/B switches of the Jacobi kernel: bit 1 = barrier per round instead of the row hand-over
   int gates_diag;     // every gate of the model is diagonal (fused phase epilogue)
   double thr_sched[4];  // threshold Jacobi: sweeps 0..3 rotate only pairs with |g|^2 / (a_i a_j) above these
+  double small_rel2;    // stopping rule: a sweep whose rotations all had |g|^2 / (a_i a_j) below this ends the iteration
+                        // (tcj::SMALL_REL2; 0 with TC_EARLY_STOP=0: iterate until a sweep rotates nothing)
   double *trunc_err;  // [R][L+1] discarded weight accumulated per bond (single writer, deterministic)
   int *flags;         // [0]: chi_cap overflow count, [1]: Jacobi non-convergence count, [2]: sweeps max
   // workspace (one layer of ws_chains chains): slot = (r - r0)*nbmax + jb

@@ -24,7 +24,6 @@
 #include "tc_gemm.cuh"
 #include "tc_jacobi.cuh"
 #include "tc_jacobi_blocked.cuh"
-#include "tc_jacobi_rb.cuh"
 #include "tc_observe.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -64,10 +63,8 @@ struct tc_ctx {
   double *small_out = nullptr;                       // 8 doubles
   bool have_model = false;
   bool blocked_attr_set = false;
-  bool rb_attr_set = false;
   bool no_small_kernel = false;  // TC_SMALL_KERNEL=0: the 128-register Jacobi kernel for narrow contexts too (A/B)
   bool qrw_attr_set = false;
-  int jacobi_kind = 1;  // TC_JACOBI = blocked (1, default: 16-warp kernel) | rb (2: register-blocked, experimental) | simple (0)
   bool force_simple_jacobi = false;  // TC_JACOBI=simple: the warp-per-pair kernel for every size (A/B testing)
   // chain groups: the chains never interact, so G groups run their periods on G streams and the tail of one group's
   // layer (fewer CTAs than SMs left) overlaps the next kernels of the others.  TC_GROUPS, default 4.
@@ -385,14 +382,7 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
     }
     {
       ProfScope ps(c, TC_PROF_JACOBI);
-      if (d.n2 <= tcr::MAX_N && c->jacobi_kind == 2) {
-        const size_t smem = tcr::smem_bytes(d.n2);
-        if (!c->rb_attr_set) {
-          CK(cudaFuncSetAttribute(tcr::jacobi_rb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          c->rb_attr_set = true;
-        }
-        tcr::jacobi_rb_kernel<<<dim3(nr, nb), tcr::NT, smem, st>>>(d, a);
-      } else if (d.n2 <= tcb::MAX_N && !c->force_simple_jacobi) {
+      if (d.n2 <= tcb::MAX_N && !c->force_simple_jacobi) {
         const size_t smem = (size_t)3 * tcb::BR * d.n2 * sizeof(cplx) + d.n2 * sizeof(double) + 64 + 2 * tcb::BR * sizeof(int);
         if (!c->blocked_attr_set) {
           CK(cudaFuncSetAttribute(tcb::jacobi_blocked_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -608,7 +598,6 @@ int tc_ctx_create(int device, int L, int chi_cap, int R, void *arena, size_t are
   if (const char *e = getenv("TC_GROUPS")) c->ngroups = atoi(e) > 0 ? atoi(e) : 1;
   if (const char *e = getenv("TC_JACOBI")) {
     c->force_simple_jacobi = strcmp(e, "simple") == 0;
-    c->jacobi_kind = strcmp(e, "simple") == 0 ? 0 : (strcmp(e, "rb") == 0 ? 2 : 1);
   }
   if (stream) {
     c->stream = (cudaStream_t)stream;
@@ -651,6 +640,9 @@ int tc_ctx_create(int device, int L, int chi_cap, int R, void *arena, size_t are
     }
     for (int k = 0; k < 4; ++k) d.thr_sched[k] = sched[k];
   }
+  d.small_rel2 = tcj::SMALL_REL2;
+  if (const char *e = getenv("TC_EARLY_STOP"))
+    if (atoi(e) == 0) d.small_rel2 = 0.0;  // A/B: run until a sweep rotates nothing (the verification sweep)
   d.trunc_err = (double *)(base + lo.trunc_err);
   d.flags = (int *)(base + lo.flags);
   d.Cw = (cplx *)(base + lo.Cw);
@@ -1015,8 +1007,7 @@ int tc_correlation(tc_ctx *c, int r, int i, int j, const double *op1_host, const
   CK(cudaMemcpyAsync(c->op_scratch + 20, lo_op, 4 * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(c->op_scratch + 24, hi_op, 4 * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  // for i == j the kernel multiplies op_lo op_hi, which must be op1 op2
-  if (i == j) return transfer(c, r, c, r, lo, hi, c->op_scratch + 20, c->op_scratch + 24, 1, out_host);
+  // for i == j the kernel multiplies op_lo op_hi = op1 op2 (no swap happened)
   return transfer(c, r, c, r, lo, hi, c->op_scratch + 20, c->op_scratch + 24, 1, out_host);
 }
 

@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(NT) jacobi_rows_kernel(TcDev d, LayerArgs a) {
         gi = warp_sum(gi);
         const double g2 = gr * gr + gi * gi;
         if (!(g2 > tol2 * ai * aj)) continue;
-        nrot += g2 > SMALL_REL2 * ai * aj;
+        nrot += g2 > fmax(tol2, d.small_rel2) * ai * aj;
         const double ga = sqrt(g2);
         const double zeta = (aj - ai) / (2.0 * ga);
         const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(NT) jacobi_rows_cluster_kernel(TcDev d, LayerA
     // threshold sweeps and their stopping rule as in tc_jacobi_blocked.cuh (here a skipped rotation also saves the
     // write-back of the two rows, half of the L2 traffic of the pair)
     const double tol2 = sweep < 4 ? fmax(tol2_final, d.thr_sched[sweep]) : tol2_final;
-    const double small2 = tol2 > tol2_final ? tol2_final : SMALL_REL2;
+    const double small2 = tol2 > tol2_final ? tol2_final : fmax(tol2_final, d.small_rel2);
     int nrot = 0;
     for (int r = 0; r < M - 1; ++r) {
       for (int k = gw; k < M / 2; k += nw) {

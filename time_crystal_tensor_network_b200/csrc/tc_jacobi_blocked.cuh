@@ -299,7 +299,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
     // stopping rule: a sweep that rotated every pair above the final tolerance and found them all below 1e-8 ends the
     // iteration (quadratic convergence: what is left is below 1e-16); a threshold sweep has skipped pairs, so there
     // anything above the final tolerance keeps the iteration going
-    const double small2 = tol2 > tol2_final ? tol2_final : tcj::SMALL_REL2;
+    const double small2 = tol2 > tol2_final ? tol2_final : fmax(tol2_final, d.small_rel2);
     int nrot = 0;
     TCC_T(c1);
     TCC_ACC(0, c0, c1);

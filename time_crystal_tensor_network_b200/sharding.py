@@ -67,3 +67,33 @@ def disorder_average(local_sum, local_count, group=None, device=None):
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     t = t.cpu().numpy()
     return t[:-1].reshape(s.shape) / t[-1]
+
+
+def run_sharded_ensemble(L, J, tau, h_fields_all, n_periods, rank=0, world_size=1, device=0, group=None, **ensemble_kw):
+    """The loop the reference runs serially over realisations (main.py:467-469), sharded: rank ``rank`` evolves its
+    contiguous block of the chains ``h_fields_all`` [n_items][L] on GPU ``device`` (one FloquetEnsemble, no
+    communication), then the records are all-gathered.  Returns Z[T][n_items][L], S_ent, LE, chi on every rank: the
+    same arrays, bit for bit, as one GPU evolving all the chains (chains never interact; the per-chain arithmetic does
+    not depend on which context or group a chain sits in)."""
+    from .engine import FloquetEnsemble
+    h = np.atleast_2d(np.asarray(h_fields_all, dtype=float))
+    n_items = h.shape[0]
+    lo, hi = shard_bounds(n_items, world_size, rank)
+    out = {}
+    if hi > lo:
+        ens = FloquetEnsemble(L, J, tau, h[lo:hi], device=device, **ensemble_kw)
+        rec = ens.run(n_periods)
+        ens.close()
+        out = {k: rec[k] for k in ('Z', 'S_ent', 'LE', 'chi')}
+    else:   # more ranks than chains: an empty shard still takes part in the collective
+        T = n_periods + 1
+        out = {'Z': np.zeros((T, 0, L)), 'S_ent': np.zeros((T, 0, max(L - 1, 0))), 'LE': np.zeros((T, 0)),
+               'chi': np.zeros((T, 0, L + 1), dtype=np.int32)}
+    if world_size == 1:        # one shard holds everything: no collective (also when a process group exists)
+        return out
+    dev = f'cuda:{device}' if device is not None else None
+    full = {}
+    for k, v in out.items():
+        a = gather_records(v.astype(np.float64) if k == 'chi' else v, n_items, axis=1, group=group, device=dev)
+        full[k] = a.astype(np.int32) if k == 'chi' else a
+    return full
