@@ -52,6 +52,13 @@ size_t tc_ctx_arena_bytes(int L, int chi_cap, int R);
    stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = a new stream.      */
 int tc_ctx_create(int device, int L, int chi_cap, int R, void *arena, size_t arena_bytes,
                   void *stream, tc_ctx **out);
+/* Storage-only variant (storage_only != 0): the arena holds the state, the model and the observable scratch but no
+   SVD workspace -- for snapshots that are only measured, copied or overlapped (the states list
+   CustomFloquet.evolve_floquet returns, src/dynamics/tebd_evolution.py:236-241).  Gate and Floquet calls on such a
+   context fail with an error; copy the chain into a full context (tc_copy_chain) to evolve it. */
+size_t tc_ctx_arena_bytes2(int L, int chi_cap, int R, int storage_only);
+int tc_ctx_create2(int device, int L, int chi_cap, int R, int storage_only, void *arena, size_t arena_bytes,
+                   void *stream, tc_ctx **out);
 int tc_ctx_destroy(tc_ctx *ctx);
 int tc_sync(tc_ctx *ctx);
 int tc_ctx_info(tc_ctx *ctx, int *L, int *chi_cap, int *R, int *device);

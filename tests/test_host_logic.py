@@ -60,6 +60,31 @@ def test_library_exports_every_declared_symbol():
     assert lib.tc_version() >= 100
     assert lib.tc_ctx_arena_bytes(32, 128, 32) > 1.5 * 1024 ** 3     # 0.5 GiB of state + 1 GiB of workspaces
     assert lib.tc_ctx_arena_bytes(0, 1, 1) == 0
+    # a storage-only context (snapshots) carries no SVD workspace: the 32-chain metric shape needs a third of the bytes,
+    # a single L = 64, chi = 256 snapshot 0.27 GB instead of 0.8 GB
+    assert lib.tc_ctx_arena_bytes2(32, 128, 32, 0) == lib.tc_ctx_arena_bytes(32, 128, 32)
+    assert lib.tc_ctx_arena_bytes2(32, 128, 32, 1) < 0.6 * 1024 ** 3
+    assert lib.tc_ctx_arena_bytes2(64, 256, 1, 1) < 0.4 * lib.tc_ctx_arena_bytes2(64, 256, 1, 0)
+
+
+def test_documented_import_routes():
+    """Every import route INTEGRATION.md documents works from a clean interpreter (no GPU needed to import)."""
+    import subprocess
+    doc = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    assert "/path/to/repo/src'" in doc and "/path/to/repo/time_crystal_tensor_network_b200'" not in doc
+    for code in (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from core.tensor_utils import create_initial_state\n"
+        "from core.observables import calculate_loschmidt_echo, magnetization, staggered_magnetization\n"
+        "from models.kicked_ising import KickedIsingModel\n"
+        "from dynamics.tebd_evolution import CustomFloquet, TEBDEvolution\n" % os.path.join(ROOT, 'src'),
+        "import sys; sys.path.insert(0, %r)\n"
+        "from time_crystal_tensor_network_b200.models.kicked_ising import KickedIsingModel\n"
+        "from time_crystal_tensor_network_b200.dynamics.tebd_evolution import CustomFloquet\n"
+        "from time_crystal_tensor_network_b200.core.observables import magnetization\n" % ROOT,
+    ):
+        out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd='/')
+        assert out.returncode == 0, out.stderr
 
 
 def test_no_cpu_fallback():

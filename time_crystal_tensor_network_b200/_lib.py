@@ -31,6 +31,8 @@ SIGNATURES = {
     'tc_device_count': (C.c_int, [C.POINTER(C.c_int)]),
     'tc_ctx_arena_bytes': (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     'tc_ctx_create': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P, C.POINTER(_P)]),
+    'tc_ctx_arena_bytes2': (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    'tc_ctx_create2': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P, C.POINTER(_P)]),
     'tc_ctx_destroy': (C.c_int, [_P]),
     'tc_sync': (C.c_int, [_P]),
     'tc_ctx_info': (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

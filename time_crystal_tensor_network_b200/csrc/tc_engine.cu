@@ -125,7 +125,7 @@ struct Layout {
   int ws_chains, nbmax, n2;
 };
 
-static Layout make_layout(int L, int chi_cap, int R) {
+static Layout make_layout(int L, int chi_cap, int R, bool storage_only = false) {
   Layout o{};
   const size_t cs = sizeof(cplx);
   o.n2 = 2 * chi_cap;
@@ -137,6 +137,7 @@ static Layout make_layout(int L, int chi_cap, int R) {
   long long wc = (long long)(budget / per_chain);
   if (wc < 1) wc = 1;
   if (wc > R) wc = R;
+  if (storage_only) wc = 0;  // snapshots: state + model + observable scratch, no SVD workspace
   o.ws_chains = (int)wc;
   const size_t slots = (size_t)o.ws_chains * o.nbmax;
   size_t p = 0;
@@ -349,6 +350,8 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
                      int diag, cudaStream_t st, int ws_lo, int ws_n) {
   if (nb <= 0 || r_hi <= r_lo) return 0;
   const TcDev &d = c->d;
+  if (d.ws_chains < 1 || ws_n < 1)
+    return fail("storage-only context (tc_ctx_create2): no SVD workspace, copy the chain into a full context to evolve it");
   const int tiles1 = (d.n2 + tcg::BM - 1) / tcg::BM;
   const int tiles = tiles1 * tiles1;
   for (int r0 = r_lo; r0 < r_hi; r0 += ws_n) {
@@ -480,6 +483,8 @@ static int run_periods_with(tc_ctx *c, int n, After &&after) {
   int G = c->ngroups;
   if (G > d.R) G = d.R;
   if (G > d.ws_chains) G = d.ws_chains;
+  if (d.ws_chains < 1)
+    return fail("storage-only context (tc_ctx_create2): no SVD workspace, copy the chain into a full context to evolve it");
   if (c->profile || G <= 1) {
     for (int t = 0; t < n; ++t) {
       if (run_period_on(c, 0, d.R, c->stream, 0, d.ws_chains)) return 1;
@@ -505,17 +510,20 @@ static int run_periods_with(tc_ctx *c, int n, After &&after) {
   for (int g = 0; g < G; ++g) CK(cudaStreamWaitEvent(c->gstreams[g], c->gfork, 0));
   // period-major enqueue order: a stream takes only so many pending launches before the host blocks; feeding one
   // group all its periods first would let that group run alone for long calls
-  for (int t = 0; t < n; ++t)
-    for (int g = 0; g < G; ++g) {
+  int rc = 0;
+  for (int t = 0; t < n && !rc; ++t)
+    for (int g = 0; g < G && !rc; ++g) {
       const int r_lo = (int)((long long)d.R * g / G), r_hi = (int)((long long)d.R * (g + 1) / G);
-      if (run_period_on(c, r_lo, r_hi, c->gstreams[g], whole ? r_lo : g * wpg, whole ? r_hi - r_lo : wpg)) return 1;
-      if (after(t, r_lo, r_hi, c->gstreams[g])) return 1;
+      rc = run_period_on(c, r_lo, r_hi, c->gstreams[g], whole ? r_lo : g * wpg, whole ? r_hi - r_lo : wpg);
+      if (!rc) rc = after(t, r_lo, r_hi, c->gstreams[g]);
     }
+  // join on the error path too: what was queued on the group streams still uses the arena, and the caller may free
+  // it as soon as the context's stream is idle
   for (int g = 0; g < G; ++g) {
     CK(cudaEventRecord(c->gjoin[g], c->gstreams[g]));
     CK(cudaStreamWaitEvent(c->stream, c->gjoin[g], 0));
   }
-  return 0;
+  return rc;
 }
 static int run_periods(tc_ctx *c, int n) {
   return run_periods_with(c, n, [](int, int, int, cudaStream_t) { return 0; });
@@ -559,17 +567,23 @@ int tc_device_count(int *count) {
 }
 long long tc_launch_count(void) { return g_launches.load(); }
 
-size_t tc_ctx_arena_bytes(int L, int chi_cap, int R) {
+size_t tc_ctx_arena_bytes2(int L, int chi_cap, int R, int storage_only) {
   if (L < 1 || chi_cap < 1 || R < 1) return 0;
-  return make_layout(L, chi_cap, R).total;
+  return make_layout(L, chi_cap, R, storage_only != 0).total;
 }
+size_t tc_ctx_arena_bytes(int L, int chi_cap, int R) { return tc_ctx_arena_bytes2(L, chi_cap, R, 0); }
 
 int tc_ctx_create(int device, int L, int chi_cap, int R, void *arena, size_t arena_bytes, void *stream, tc_ctx **out) {
+  return tc_ctx_create2(device, L, chi_cap, R, 0, arena, arena_bytes, stream, out);
+}
+
+int tc_ctx_create2(int device, int L, int chi_cap, int R, int storage_only, void *arena, size_t arena_bytes,
+                   void *stream, tc_ctx **out) {
   if (!out) return fail("tc_ctx_create: out is null");
   if (L < 1 || chi_cap < 1 || R < 1) return fail("tc_ctx_create: L, chi_cap, R must be >= 1");
   if (R > 65535) return fail("tc_ctx_create: R > 65535 chains per context");
   CK(cudaSetDevice(device));
-  Layout lo = make_layout(L, chi_cap, R);
+  Layout lo = make_layout(L, chi_cap, R, storage_only != 0);
   tc_ctx *c = new tc_ctx();
   c->device = device;
   if (arena) {

@@ -30,13 +30,18 @@ class CustomFloquet:
         """Returns (states, times, info); a state is stored after period p when p % measure_every == 0
         (0-based), times are (p + 1) * 2 tau (tebd_evolution.py:218-259)."""
         top = lambda psi: max(psi.chi) if psi.chi else 1
-        states, times, bond_dims = [psi_initial.copy()], [0.0], [top(psi_initial)]
+        # one working state advances in place when the model offers it (KickedIsingModel.floquet_step_inplace: the same
+        # arithmetic as floquet_step without a new context per period); the returned states are snapshots without SVD
+        # workspace.  Any other model object goes through its floquet_step as in the reference.
+        snap = lambda psi: psi.copy(storage=True) if isinstance(psi, MPS) else psi.copy()
+        step = getattr(self.model, 'floquet_step_inplace', None) or self.model.floquet_step
+        states, times, bond_dims = [snap(psi_initial)], [0.0], [top(psi_initial)]
         psi = psi_initial.copy()
         t0 = time.time()
         for period in range(n_periods):
-            psi = self.model.floquet_step(psi, self.trunc_params)
+            psi = step(psi, self.trunc_params)
             if period % measure_every == 0:
-                states.append(psi.copy())
+                states.append(snap(psi))
                 times.append((period + 1) * 2 * self.model.tau)
                 bond_dims.append(top(psi))
         wall = time.time() - t0
@@ -104,7 +109,7 @@ class TEBDEvolution:
         psi._ctx.set_trunc('tebd', chi_max=chi_max, svd_min=tp.get('svd_min') or 0.0,
                            trunc_cut=tp.get('trunc_cut') or 0.0)
         psi._ctx.trunc_err(reset=True)
-        states, times = [psi_initial.copy()], [0.0]
+        states, times = [psi_initial.copy(storage=True)], [0.0]
         bond_dims, entropies, errs = [psi_initial.chi], [psi_initial.entanglement_entropy()], []
         t0 = time.time()
         for step in range(n_steps):
@@ -115,7 +120,7 @@ class TEBDEvolution:
                 psi._ctx.apply_layer(0, 0)
             psi._touch()
             if step % observe_every == 0:
-                states.append(psi.copy())
+                states.append(psi.copy(storage=True))
                 times.append((step + 1) * dt)
                 bond_dims.append(psi.chi)
                 entropies.append(psi.entanglement_entropy())

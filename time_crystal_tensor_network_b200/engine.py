@@ -24,19 +24,23 @@ def _torch():
 class Context:
     """R independent chains of L sites, bond dimension at most chi_cap, on one GPU."""
 
-    def __init__(self, L, chi_cap, R=1, device=0):
+    def __init__(self, L, chi_cap, R=1, device=0, storage_only=False):
+        """storage_only: a context without SVD workspace (snapshots that are only measured, copied or overlapped);
+        gate and Floquet calls on it raise."""
         torch = _torch()
         self.lib = _lib.load()
         self.L, self.chi_cap, self.R, self.device = int(L), int(chi_cap), int(R), int(device)
-        nbytes = self.lib.tc_ctx_arena_bytes(self.L, self.chi_cap, self.R)
+        self.storage_only = bool(storage_only)
+        nbytes = self.lib.tc_ctx_arena_bytes2(self.L, self.chi_cap, self.R, int(self.storage_only))
         if nbytes == 0:
             raise ValueError(f'invalid context shape L={L}, chi_cap={chi_cap}, R={R}')
         self.stream = torch.cuda.Stream(device=self.device)
         with torch.cuda.device(self.device):
             self._arena = torch.empty(nbytes, dtype=torch.uint8, device=f'cuda:{self.device}')
         handle = C.c_void_p()
-        check(self.lib.tc_ctx_create(self.device, self.L, self.chi_cap, self.R, self._arena.data_ptr(), nbytes,
-                                     self.stream.cuda_stream, C.byref(handle)), 'tc_ctx_create')
+        check(self.lib.tc_ctx_create2(self.device, self.L, self.chi_cap, self.R, int(self.storage_only),
+                                      self._arena.data_ptr(), nbytes, self.stream.cuda_stream, C.byref(handle)),
+              'tc_ctx_create2')
         self._h = handle
         self.arena_bytes = nbytes
 

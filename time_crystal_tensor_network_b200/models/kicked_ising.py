@@ -65,11 +65,13 @@ class KickedIsingModel:
         return dict(mode='reference', cutoff=1e-13)
 
     def _room_for_one_period(self, psi, settings):
-        """Bond dimension the context must be able to hold after one period: each bond is updated
-        twice and an update at most doubles it."""
+        """Bond dimension the context must be able to hold after one period: each bond is updated twice and an
+        update multiplies it by at most the operator-Schmidt rank of its gate (2 for the diagonal Ising gates
+        _prepare_gates builds, up to 4 for general 4x4 matrices a user assigned to ``ising_gates``)."""
         L = psi.L
         now = max(psi._chi_full())
-        cap = min(2 ** (L // 2), 4 * now)
+        diag = all(np.count_nonzero(g - np.diag(np.diag(g))) == 0 for g in self.ising_gates)
+        cap = min(2 ** (L // 2), (4 if diag else 16) * now)
         if settings['mode'] == 'tebd' and settings['chi_max'] > 0:
             cap = min(cap, settings['chi_max'])
         cap = max(cap, now, 1)
@@ -89,15 +91,27 @@ class KickedIsingModel:
         psi._ctx.set_model(gates, np.asarray(self.pi_pulse_gate, dtype=complex).reshape(1, 2, 2))
         psi._ctx.set_trunc(**settings)
 
+    @staticmethod
+    def _check_flags(psi):
+        fl = psi._ctx.flags()
+        if fl['chi_cap_overflow'] or fl['svd_not_converged']:
+            raise EngineError(f'update failed on the device: {fl}')
+
     def _advance(self, psi, settings):
         """One period in place on ``psi`` (which this module owns)."""
         psi._grow(self._room_for_one_period(psi, settings))
         self._load(psi, settings)
         psi._ctx.floquet_step(1)
         psi._touch()
-        fl = psi._ctx.flags()
-        if fl['chi_cap_overflow'] or fl['svd_not_converged']:
-            raise EngineError(f'Floquet step failed on the device: {fl}')
+        self._check_flags(psi)
+
+    def floquet_step_inplace(self, psi: MPS, trunc_params: Dict = None) -> MPS:
+        """One Floquet period applied to ``psi`` itself (no new context): what the time loops of ``evolve`` and
+        ``CustomFloquet.evolve_floquet`` use on their private working copy.  Same arithmetic as ``floquet_step``."""
+        if trunc_params is None:
+            trunc_params = {'chi_max': 100, 'svd_min': 1e-12}
+        self._advance(psi, self._trunc_settings(trunc_params))
+        return psi
 
     # ------------------------------------------------------------------ public API
     def floquet_step(self, psi: MPS, trunc_params: Dict = None) -> MPS:
@@ -118,6 +132,7 @@ class KickedIsingModel:
         if self.n_sites > 2:
             out._ctx.apply_layer(1, 0)
         out._touch()
+        self._check_flags(out)
         return out
 
     def _apply_pi_pulse(self, psi: MPS, trunc_params: Dict = None) -> MPS:
@@ -144,11 +159,12 @@ class KickedIsingModel:
         if trunc_params is None:
             trunc_params = {'chi_max': 100, 'svd_min': 1e-12}
         settings = self._trunc_settings(trunc_params)
-        states, times = [psi_initial.copy()], [0.0]
+        # one working context advances in place; the returned states are snapshots without SVD workspace
+        states, times = [psi_initial.copy(storage=True)], [0.0]
         work = psi_initial.copy()
         for step in range(n_steps):
             self._advance(work, settings)
-            states.append(work.copy())
+            states.append(work.copy(storage=True))
             times.append((step + 1) * 2 * self.tau)
         return states, times
 

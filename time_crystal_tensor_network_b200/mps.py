@@ -38,7 +38,9 @@ class SpinHalfSite:
 
     def __init__(self, conserve='Sz', sort_charge=None):
         self.conserve = conserve
-        self._up = UP_INDEX if conserve == 'parity' else 0
+        # TeNPy >= 1.0 sorts the charges of both conserving variants (sort_charge=True), which puts 'up' at index 1;
+        # without conservation the order stays ['up', 'down']
+        self._up = UP_INDEX if conserve in ('parity', 'Sz') else 0
         self.leg = _Leg(conserve)
         self.state_labels = {'up': self._up, 'down': 1 - self._up}
 
@@ -88,18 +90,22 @@ class MPS:
         ctx.set_product_state(np.array(idx, dtype=np.int8)[None, :])
         return cls(ctx, sites)
 
-    def copy(self, chi_cap=None):
-        """New, independent state with the same tensors (optionally with room for larger bonds)."""
+    def copy(self, chi_cap=None, storage=False):
+        """New, independent state with the same tensors (optionally with room for larger bonds).
+        storage=True: a snapshot in a context without SVD workspace (tensors, Schmidt values and observable scratch
+        only, sized to the current bond dimensions); it is measured, overlapped and copied like any other state and
+        moves to a full context by itself the first time a gate is applied to it."""
         cap = max(int(chi_cap or 0), max(self._chi_full()), 1)
-        ctx = Context(self.L, cap, 1, self._ctx.device)
+        ctx = Context(self.L, cap, 1, self._ctx.device, storage_only=storage)
         ctx.copy_chain_from(0, self._ctx, 0)
         out = MPS(ctx, self.sites)
         out.norm = self.norm
         return out
 
     def _grow(self, chi_cap):
-        if chi_cap > self._ctx.chi_cap:
-            ctx = Context(self.L, chi_cap, 1, self._ctx.device)
+        """Make sure the state sits in a full (evolvable) context that can hold bonds up to chi_cap."""
+        if chi_cap > self._ctx.chi_cap or self._ctx.storage_only:
+            ctx = Context(self.L, max(chi_cap, self._ctx.chi_cap), 1, self._ctx.device)
             ctx.copy_chain_from(0, self._ctx, 0)
             self._ctx.close()
             self._ctx = ctx
@@ -230,12 +236,18 @@ class MPS:
             data[f'B{i}'] = self.get_B(i, 'B')
         for b in range(self.L + 1):
             data[f'S{b}'] = self._ctx.get_S(0, b)
-        np.savez(path, **data)
+        np.savez(self._npz_path(path), **data)
+
+    @staticmethod
+    def _npz_path(path):
+        """np.savez appends '.npz' to a name without it; save and load agree on the final name."""
+        path = os.fspath(path)
+        return path if path.endswith('.npz') else path + '.npz'
 
     @classmethod
     def load(cls, path, device=0):
         """Inverse of :meth:`save`."""
-        with np.load(path, allow_pickle=False) as z:
+        with np.load(cls._npz_path(path), allow_pickle=False) as z:
             L = int(z['L'])
             Bs = [z[f'B{i}'] for i in range(L)]
             Ss = [z[f'S{b}'] for b in range(L + 1)]
