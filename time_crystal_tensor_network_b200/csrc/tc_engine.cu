@@ -64,7 +64,7 @@ struct tc_ctx {
   bool have_model = false;
   bool blocked_attr_set = false;
   bool no_small_kernel = false;  // TC_SMALL_KERNEL=0: the 128-register Jacobi kernel for narrow contexts too (A/B)
-  bool qrw_attr_set = false;
+  bool qrw_attr_set = false, qr_attr_set = false;
   bool force_simple_jacobi = false;  // TC_JACOBI=simple: the warp-per-pair kernel for every size (A/B testing)
   // chain groups: the chains never interact, so G groups run their periods on G streams and the tail of one group's
   // layer (fewer CTAs than SMs left) overlaps the next kernels of the others.  TC_GROUPS, default 4.
@@ -370,14 +370,19 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
     {
       ProfScope ps(c, TC_PROF_QR);
       if (d.n2 <= tcj::QMAXM && !c->force_simple_jacobi) {
-        tcj::qr_blocked_kernel<tcj::QNT><<<dim3(nr, nb), tcj::QNT, tcj::QNT * tcj::QB * sizeof(cplx), st>>>(d, a);
+        const int smem = tcj::QNT * tcj::QBDEF * (int)sizeof(cplx);  // V panel
+        if (!c->qr_attr_set) {
+          CK(cudaFuncSetAttribute(tcj::qr_blocked_kernel<tcj::QNT, tcj::QBDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+          c->qr_attr_set = true;
+        }
+        tcj::qr_blocked_kernel<tcj::QNT, tcj::QBDEF><<<dim3(nr, nb), tcj::QNT, smem, st>>>(d, a);
       } else if (d.n2 <= tcj::QMAXMW && !c->force_simple_jacobi) {
-        const int smem = tcj::QNTW * tcj::QB * (int)sizeof(cplx);  // 64 KB V panel
+        const int smem = tcj::QNTW * tcj::QBDEF * (int)sizeof(cplx);  // V panel
         if (!c->qrw_attr_set) {
-          CK(cudaFuncSetAttribute(tcj::qr_blocked_kernel<tcj::QNTW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+          CK(cudaFuncSetAttribute(tcj::qr_blocked_kernel<tcj::QNTW, tcj::QBDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
           c->qrw_attr_set = true;
         }
-        tcj::qr_blocked_kernel<tcj::QNTW><<<dim3(nr, nb), tcj::QNTW, smem, st>>>(d, a);
+        tcj::qr_blocked_kernel<tcj::QNTW, tcj::QBDEF><<<dim3(nr, nb), tcj::QNTW, smem, st>>>(d, a);
       } else {
         tcj::qr_kernel<<<dim3(nb, nr), tcj::NT, (d.n2 + 64) * sizeof(cplx), st>>>(d, a);
       }
@@ -386,7 +391,7 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
     {
       ProfScope ps(c, TC_PROF_JACOBI);
       if (d.n2 <= tcb::MAX_N && !c->force_simple_jacobi) {
-        const size_t smem = (size_t)3 * tcb::BR * d.n2 * sizeof(cplx) + d.n2 * sizeof(double) + 64 + 2 * tcb::BR * sizeof(int);
+        const size_t smem = (size_t)3 * tcb::BR * d.n2 * sizeof(cplx) + d.n2 * sizeof(double2) + 64 + 2 * tcb::BR * sizeof(int);
         if (!c->blocked_attr_set) {
           CK(cudaFuncSetAttribute(tcb::jacobi_blocked_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
           CK(cudaFuncSetAttribute(tcb::jacobi_blocked_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -156,8 +156,14 @@ __device__ __forceinline__ void tcg_dmma(double &c0, double &c1, double a, doubl
                : "d"(a), "d"(b));
 }
 
-constexpr int QB = 8, QNT = 256, QMAXM = 256;  // fast-path instance: M <= 256 rows, 256 threads
-constexpr int QNTW = 512, QMAXMW = 512;         // wide instance (chi_cap <= 256): M <= 512 rows, 512 threads
+constexpr int QNT = 256, QMAXM = 256;    // fast-path instance: M <= 256 rows, 256 threads
+constexpr int QNTW = 512, QMAXMW = 512;  // wide instance (chi_cap <= 256): M <= 512 rows, 512 threads
+#ifndef TC_QB
+#define TC_QB 8
+#endif
+constexpr int QBDEF = TC_QB;  // panel width (8 or 16 columns).  16 halves the passes over the trailing matrix but was measured
+                              // slower on the B200 (QR share of the step 6.9 % -> 10.0 %, r02d): the kernel is bound by the panel
+                              // factorisation (block reductions, V^H V, T) and not by the trailing update
 
 // block-wide sums of NV doubles per thread; result in out[0..NV) (all threads), scratch [QT/32][NV]
 template <int NV, int QT>
@@ -183,8 +189,8 @@ __device__ __forceinline__ void block_sum_vec(double (&v)[NV], double *scratch, 
     }
 }
 
-// QT threads = max rows; dynamic smem: V panel, QT * QB cplx
-template <int QT>
+// QT threads = max rows, QB = panel width (multiple of 8); dynamic smem: V panel, QT * QB cplx
+template <int QT, int QB>
 __global__ void __launch_bounds__(QT) qr_blocked_kernel(TcDev d, LayerArgs a) {
   Bond b;
   // blockIdx.x = chain, blockIdx.y = rank of the bond in centre-out order (largest matrices first)
@@ -196,6 +202,7 @@ __global__ void __launch_bounds__(QT) qr_blocked_kernel(TcDev d, LayerArgs a) {
   __shared__ __align__(16) cplx Tm[QB * QB];
   __shared__ double scratch[(QT / 32) * 2 * QB];
   __shared__ cplx s_alpha;
+  __shared__ cplx s_tau[QB];
   const int tid = threadIdx.x;
   const int steps = (M - 1) < N ? (M - 1) : N;  // columns that have something to annihilate
   for (int k0 = 0; k0 < steps; k0 += QB) {
@@ -206,10 +213,9 @@ __global__ void __launch_bounds__(QT) qr_blocked_kernel(TcDev d, LayerArgs a) {
     cplx p[QB];
 #pragma unroll
     for (int j = 0; j < QB; ++j) p[j] = (have && j < pw) ? X[(size_t)(k0 + tid) * N + k0 + j] : cmake(0.0, 0.0);
-    cplx tau[QB];
 #pragma unroll
     for (int j = 0; j < QB; ++j) {
-      tau[j] = cmake(0.0, 0.0);
+      cplx tauj = cmake(0.0, 0.0);
       if (j < nbw) {
         // |x|^2 below the diagonal of column j
         double red[2 * QB];
@@ -218,10 +224,10 @@ __global__ void __launch_bounds__(QT) qr_blocked_kernel(TcDev d, LayerArgs a) {
         block_sum_vec<2 * QB, QT>(red, scratch, 1);
         double beta;
         cplx sc;
-        larfg(s_alpha, red[0], beta, tau[j], sc);
+        larfg(s_alpha, red[0], beta, tauj, sc);
         const cplx v = (tid == j) ? cmake(1.0, 0.0) : ((have && tid > j) ? cmul(p[j], sc) : cmake(0.0, 0.0));
         V[tid * QB + j] = v;
-        if (tau[j].x != 0.0 || tau[j].y != 0.0) {
+        if (tauj.x != 0.0 || tauj.y != 0.0) {
           // w_c = conj(tau) sum_r conj(v_r) p_r[c] for the remaining panel columns
 #pragma unroll
           for (int c = 0; c < QB; ++c) {
@@ -231,7 +237,7 @@ __global__ void __launch_bounds__(QT) qr_blocked_kernel(TcDev d, LayerArgs a) {
             red[2 * c + 1] = t.y;
           }
           block_sum_vec<2 * QB, QT>(red, scratch, 2 * QB);
-          const cplx tc = cconj(tau[j]);
+          const cplx tc = cconj(tauj);
 #pragma unroll
           for (int c = 0; c < QB; ++c)
             if (c > j) {
@@ -248,6 +254,7 @@ __global__ void __launch_bounds__(QT) qr_blocked_kernel(TcDev d, LayerArgs a) {
       } else {
         V[tid * QB + j] = cmake(0.0, 0.0);
       }
+      if (tid == 0) s_tau[j] = tauj;
     }
     // R part of the panel back to global
     if (have)
@@ -270,54 +277,68 @@ __global__ void __launch_bounds__(QT) qr_blocked_kernel(TcDev d, LayerArgs a) {
         }
       }
       __syncthreads();
-      if (tid == 0) {
+      if (warp == 0) {  // column after column, lane i computes row i of the column (rows are independent)
         for (int j = 0; j < QB; ++j) {
-          for (int i = 0; i < QB; ++i) Tm[i * QB + j] = cmake(0.0, 0.0);
-          Tm[j * QB + j] = tau[j];
-          for (int i = 0; i < j; ++i) {
-            cplx acc = cmake(0.0, 0.0);
-            for (int l = i; l < j; ++l) cfma(acc, Tm[i * QB + l], G[l * QB + j]);
-            const cplx mt = cmake(-tau[j].x, -tau[j].y);
-            Tm[i * QB + j] = cmul(mt, acc);
+          const cplx tj = s_tau[j];
+          if (lane < QB) {
+            cplx t = cmake(0.0, 0.0);
+            if (lane == j) t = tj;
+            if (lane < j) {
+              cplx acc = cmake(0.0, 0.0);
+              for (int l = lane; l < j; ++l) cfma(acc, Tm[lane * QB + l], G[l * QB + j]);
+              t = cmul(cmake(-tj.x, -tj.y), acc);
+            }
+            Tm[lane * QB + j] = t;
           }
+          __syncwarp();
         }
       }
       __syncthreads();
     }
     // ---- trailing columns: A <- (I - V T^H V^H) A on the FP64 tensor pipe (mma.sync m8n8k4.f64 = DMMA; same FP64
     // peak as DFMA on sm_100a, but one warp instruction per 256 FMAs and no shared-memory broadcast per FMA).
-    // A warp owns tiles of 8 trailing columns.  Pass 1, W = V^H A: M = 8 reflectors, K = rows, N = 8 columns (A operand
-    // conj(V)^T from shared memory, B operand the trailing matrix straight from L2).  W2 = T^H W per lane from a per-warp
-    // scratch, directly in the B-operand layout of pass 2, A -= V W2: M = 8 rows, K = 8 reflectors, N = 8 columns.
+    // A warp owns tiles of 8 trailing columns.  Pass 1, W = V^H A: M = QB reflectors (QB / 8 tiles), K = rows, N = 8
+    // columns (A operand conj(V)^T from shared memory, B operand the trailing matrix straight from L2).  W2 = T^H W per
+    // lane from a per-warp scratch, directly in the B-operand layout of pass 2, A -= V W2: M = 8 rows, K = QB
+    // reflectors, N = 8 columns.
     {
-      __shared__ __align__(16) cplx Wsm[(QT / 32) * 64];
+      constexpr int MT = QB / 8, KC = QB / 4;
+      __shared__ __align__(16) cplx Wsm[(QT / 32) * QB * 8];
       const int lane = tid & 31, warp = tid >> 5, fr = lane >> 2, fk = lane & 3;
       const int ncols = N - (k0 + QB);
       const int ntiles = (ncols + 7) / 8;
       cplx *At = X + (size_t)k0 * N + k0 + QB;  // trailing block: row r (relative to k0), column cc (relative to k0 + QB)
-      cplx *Ws = Wsm + warp * 64;
+      cplx *Ws = Wsm + warp * QB * 8;
       for (int ct = warp; ct < ntiles; ct += QT / 32) {
         const int c0 = ct * 8;
         const bool cok = c0 + fr < ncols;
-        double wre[2] = {0.0, 0.0}, wim[2] = {0.0, 0.0};
+        double wre[MT][2], wim[MT][2];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) wre[mt][0] = wre[mt][1] = wim[mt][0] = wim[mt][1] = 0.0;
 #pragma unroll 4
         for (int r0 = 0; r0 < rows; r0 += 4) {
           const int r = r0 + fk;
           const bool rok = r < rows;
           const cplx av = (cok && rok) ? At[(size_t)r * N + c0 + fr] : cmake(0.0, 0.0);
-          const cplx v = rok ? V[r * QB + fr] : cmake(0.0, 0.0);
-          tcg_dmma(wre[0], wre[1], v.x, av.x);  // conj(v) a = (vx ax + vy ay) + i (vx ay - vy ax)
-          tcg_dmma(wre[0], wre[1], v.y, av.y);
-          tcg_dmma(wim[0], wim[1], v.x, av.y);
-          tcg_dmma(wim[0], wim[1], -v.y, av.x);
-        }
-        // C layout: this lane holds W[j = fr][c = 2 fk, 2 fk + 1]
-        Ws[fr * 8 + 2 * fk] = cmake(wre[0], wim[0]);
-        Ws[fr * 8 + 2 * fk + 1] = cmake(wre[1], wim[1]);
-        __syncwarp();
-        cplx w2[2];  // W2[i = 4 kc + fk][c = fr] = sum_{j <= i} conj(T[j][i]) W[j][c]
 #pragma unroll
-        for (int kc = 0; kc < 2; ++kc) {
+          for (int mt = 0; mt < MT; ++mt) {
+            const cplx v = rok ? V[r * QB + mt * 8 + fr] : cmake(0.0, 0.0);
+            tcg_dmma(wre[mt][0], wre[mt][1], v.x, av.x);  // conj(v) a = (vx ax + vy ay) + i (vx ay - vy ax)
+            tcg_dmma(wre[mt][0], wre[mt][1], v.y, av.y);
+            tcg_dmma(wim[mt][0], wim[mt][1], v.x, av.y);
+            tcg_dmma(wim[mt][0], wim[mt][1], -v.y, av.x);
+          }
+        }
+        // C layout: this lane holds W[j = 8 mt + fr][c = 2 fk, 2 fk + 1]
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          Ws[(mt * 8 + fr) * 8 + 2 * fk] = cmake(wre[mt][0], wim[mt][0]);
+          Ws[(mt * 8 + fr) * 8 + 2 * fk + 1] = cmake(wre[mt][1], wim[mt][1]);
+        }
+        __syncwarp();
+        cplx w2[KC];  // W2[i = 4 kc + fk][c = fr] = sum_{j <= i} conj(T[j][i]) W[j][c]
+#pragma unroll
+        for (int kc = 0; kc < KC; ++kc) {
           const int i = 4 * kc + fk;
           cplx acc = cmake(0.0, 0.0);
 #pragma unroll
@@ -336,7 +357,7 @@ __global__ void __launch_bounds__(QT) qr_blocked_kernel(TcDev d, LayerArgs a) {
           const cplx a1 = (rok && cc + 1 < ncols) ? ap[1] : cmake(0.0, 0.0);
           double cre[2] = {a0.x, a1.x}, cim[2] = {a0.y, a1.y};
 #pragma unroll
-          for (int kc = 0; kc < 2; ++kc) {
+          for (int kc = 0; kc < KC; ++kc) {
             const cplx v = rok ? V[r * QB + 4 * kc + fk] : cmake(0.0, 0.0);
             tcg_dmma(cre[0], cre[1], -v.x, w2[kc].x);  // a - v w2
             tcg_dmma(cre[0], cre[1], v.y, w2[kc].y);

@@ -9,9 +9,13 @@
 //   back to shared memory, p rows never leave registers; rows pass from warp to warp through per-row
 //   version counters (acquire / release), a barrier per round only with TC_ROT64 bit 1.
 // While visit (p, q) computes, the bulk load of q+1 and the bulk store of q-1 are in flight.
-// Per pair: 4 KB LDS + 4 KB STS and 167 FP64 instructions per lane (32 dot, 96 rotation, ~39 reduction and set-up:
-// the minimum for standard rotations), 271 SASS instructions in all; L2 traffic per sweep ~ (K/16)^2/2 blocks.
-// ncu (profiles/r01d_ncu_kernels.txt): FP64 pipe 51 % busy, shared-memory wavefronts 49 %, issue slots 46 %.
+// Rotations are FAST (scaled) rotations: every row carries a squared scale w (true row = sqrt(w) x stored row), the
+// factor cos of a rotation goes into w instead of into the 2 N elements, and the update is u -= A g v, v += B conj(g) u:
+// 8 instead of 12 FMAs per complex element.  A row's scale is folded back into its elements once per sweep, when its
+// block leaves the P stage.  Per pair: 4 KB LDS + 4 KB STS and ~141 FP64 instructions per lane (32 dot, 64 rotation,
+// ~45 reduction and set-up); L2 traffic per sweep ~ (K/16)^2/2 blocks.
+// ncu of the standard-rotation version (profiles/r01d_ncu_kernels.txt): FP64 pipe 51 % busy, shared-memory
+// wavefronts 49 %, issue slots 46 %.
 #pragma once
 #include "tc_common.cuh"
 #include "tc_jacobi.cuh"
@@ -85,7 +89,7 @@ __device__ unsigned long long g_tcb_timing[8];
 #endif
 
 struct Rot {
-  double cs, sr, si, ni, nj;  // cos, s*e (complex), new squared norms
+  double ar, ai, br, bi, c2, ni, nj;  // A g and B g (see make_rot), cos^2, new squared norms
 };
 
 // 1/sqrt(x) for normal positive x without the special-case branch of rsqrt(double): hardware seed (MUFU.RSQ64H,
@@ -102,15 +106,16 @@ __device__ __forceinline__ double rsqrt_nb(double x) {
   return y;
 }
 
-// Rotation that orthogonalises two rows with squared norms ai, aj and g = x_i . conj(x_j); false when the pair is
-// below the threshold or one of the rows is numerically zero (`alive` false).
-// FP64 set-up with two rsqrt and no division / sqrt / |g|.  With dd = aj - ai and 2r = sqrt(dd^2 + 4|g|^2):
-// c^2 = 1/2 + |dd|/(4r),  s e = sign(dd) g / (2 r c),  t|g| = s|g|/c = sign(dd) |g|^2 / (2 r c^2) (the amount of
-// squared norm that moves between the rows).  (An FP32/SFU angle with an FP64 cosine was measured slower on the
-// B200 and cost a tenth of a sweep; it is gone.)
-__device__ __forceinline__ bool make_rot(bool alive, double ai, double aj, double gr, double gi, double thr2,
-                                         double small2, Rot &r, int &big) {
-  const double g2 = gr * gr + gi * gi;
+// Fast rotation that orthogonalises two rows X_i = sqrt(wi) u, X_j = sqrt(wj) v with true squared norms ai, aj and
+// stored-row product (gr, gi) = u . conj(v); false when the pair is below the threshold or one of the rows is
+// numerically zero (`alive` false).  True quantities: g = sqrt(wi wj) (gr, gi), dd = aj - ai, 2r = sqrt(dd^2 + 4|g|^2),
+// c^2 = 1/2 + |dd|/(4r), s e = sign(dd) g / (2 r c).  The standard update X_i' = c X_i - (s e) X_j,
+// X_j' = conj(s e) X_i + c X_j becomes, with the factor c moved into the scales (wi' = c^2 wi, wj' = c^2 wj),
+//   u' = u - A (gr, gi) v,   v' = v + B conj(gr, gi) u,   A = wj k,  B = wi k,  k = sign(dd) / (2 r c^2):
+// FP64 set-up with two rsqrt and no division / sqrt / |g|; t|g| = |g|^2 k is the squared norm that moves between the rows.
+__device__ __forceinline__ bool make_rot(bool alive, double ai, double aj, double wi, double wj, double gr, double gi,
+                                         double thr2, double small2, Rot &r, int &big) {
+  const double g2 = (wi * wj) * fma(gr, gr, gi * gi);
   const double aa = ai * aj;
   // `big` = the pair keeps the iteration going (stopping rule), whether or not this sweep rotates it
   big = alive && g2 > small2 * aa;
@@ -119,23 +124,26 @@ __device__ __forceinline__ bool make_rot(bool alive, double ai, double aj, doubl
   const double rinv = rsqrt_nb(fma(dd, dd, 4.0 * g2));  // 1 / (2r)
   const double c2 = fma(0.5 * fabs(dd), rinv, 0.5);
   const double cinv = rsqrt_nb(c2);
-  r.cs = c2 * cinv;
-  const double ks = copysign(rinv * cinv, dd);
-  r.sr = ks * gr;
-  r.si = ks * gi;
-  const double tg = g2 * ks * cinv;
+  const double k = copysign(rinv * cinv, dd) * cinv;
+  const double A = wj * k, B = wi * k;
+  r.ar = A * gr;
+  r.ai = A * gi;
+  r.br = B * gr;
+  r.bi = B * gi;
+  r.c2 = c2;
+  const double tg = g2 * k;
   r.ni = ai - tg;
   r.nj = aj + tg;
   return true;
 }
 
 __device__ __forceinline__ void rot_apply(cplx &u, cplx &v, const Rot &r) {
-  // u' = c u - (s e) v ;  v' = conj(s e) u + c v
+  // u' = u - (ar + i ai) v ;  v' = v + (br - i bi) u
   cplx un, vn;
-  un.x = fma(r.cs, u.x, fma(-r.sr, v.x, r.si * v.y));
-  un.y = fma(r.cs, u.y, -fma(r.sr, v.y, r.si * v.x));
-  vn.x = fma(r.cs, v.x, fma(r.sr, u.x, r.si * u.y));
-  vn.y = fma(r.cs, v.y, fma(r.sr, u.y, -r.si * u.x));
+  un.x = fma(-r.ar, v.x, fma(r.ai, v.y, u.x));
+  un.y = fma(-r.ar, v.y, fma(-r.ai, v.x, u.y));
+  vn.x = fma(r.br, u.x, fma(r.bi, u.y, v.x));
+  vn.y = fma(r.br, u.y, fma(-r.bi, u.x, v.y));
   u = un;
   v = vn;
 }
@@ -154,9 +162,9 @@ __device__ __forceinline__ void warp_sum2(double &a, double &b) {
   b = hi ? k : other;
 }
 
-// both rows in shared memory (internal pairs of a block)
+// both rows in shared memory (internal pairs of a block); ni / nj point at the rows' {squared norm, squared scale}
 template <int NPL, bool FULL>
-__device__ __forceinline__ int pair_smem(cplx *xi, cplx *xj, int N, int lane, double *ni, double *nj, double dead,
+__device__ __forceinline__ int pair_smem(cplx *xi, cplx *xj, int N, int lane, double2 *ni, double2 *nj, double dead,
                                          double tol2, double small2) {
   cplx u[NPL], v[NPL];
   double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
@@ -170,12 +178,12 @@ __device__ __forceinline__ int pair_smem(cplx *xi, cplx *xj, int N, int lane, do
     h0 = fma(u[e].y, v[e].x, h0);
     h1 = fma(-u[e].x, v[e].y, h1);
   }
-  const double ai = *ni, aj = *nj;
+  const double2 si = *ni, sj = *nj;
   double gr = g0 + g1, gi = h0 + h1;
   warp_sum2(gr, gi);
   Rot r;
   int big;
-  if (!make_rot(ai > dead && aj > dead, ai, aj, gr, gi, tol2, small2, r, big)) return big;
+  if (!make_rot(si.x > dead && sj.x > dead, si.x, sj.x, si.y, sj.y, gr, gi, tol2, small2, r, big)) return big;
 #pragma unroll
   for (int e = 0; e < NPL; ++e) {
     const int c = lane + 32 * e;
@@ -186,17 +194,18 @@ __device__ __forceinline__ int pair_smem(cplx *xi, cplx *xj, int N, int lane, do
     }
   }
   if (lane == 0) {
-    *ni = r.ni;
-    *nj = r.nj;
+    *ni = make_double2(r.ni, si.y * r.c2);
+    *nj = make_double2(r.nj, sj.y * r.c2);
   }
   return big | (1 << 16);  // bits 0..15 count the pairs that keep the iteration going, bits 16.. the rotations made
 }
 
-// row i in registers (u, its squared norm ai too), row j in shared memory.  The row is loaded before anything is
-// decided: its LDS latency overlaps the norm load, and a numerically zero row (rare) just costs its dot product.
+// row i in registers (u, its squared norm ai and squared scale wi too), row j in shared memory.  The row is loaded
+// before anything is decided: its LDS latency overlaps the norm load, and a numerically zero row (rare) just costs its
+// dot product.
 template <int NPL, bool FULL>
-__device__ __forceinline__ int pair_reg(cplx (&u)[NPL], cplx *xj, int N, int lane, double &ai, double *nj, double dead,
-                                        double tol2, double small2
+__device__ __forceinline__ int pair_reg(cplx (&u)[NPL], cplx *xj, int N, int lane, double &ai, double &wi, double2 *nj,
+                                        double dead, double tol2, double small2
 #ifdef TCB_TIMING
                                         , long long (&tacc)[8]
 #endif
@@ -213,7 +222,7 @@ __device__ __forceinline__ int pair_reg(cplx (&u)[NPL], cplx *xj, int N, int lan
     h0 = fma(u[e].y, v[e].x, h0);
     h1 = fma(-u[e].x, v[e].y, h1);
   }
-  const double aj = *nj;
+  const double2 sj = *nj;
   double gr = g0 + g1, gi = h0 + h1;
   TCB_T(t1);
   warp_sum2(gr, gi);
@@ -225,7 +234,7 @@ __device__ __forceinline__ int pair_reg(cplx (&u)[NPL], cplx *xj, int N, int lan
 #endif
   Rot r;
   int big;
-  if (!make_rot(ai > dead && aj > dead, ai, aj, gr, gi, tol2, small2, r, big)) return big;
+  if (!make_rot(ai > dead && sj.x > dead, ai, sj.x, wi, sj.y, gr, gi, tol2, small2, r, big)) return big;
   TCB_T(t3);
 #pragma unroll
   for (int e = 0; e < NPL; ++e) {
@@ -234,7 +243,8 @@ __device__ __forceinline__ int pair_reg(cplx (&u)[NPL], cplx *xj, int N, int lan
     if (FULL || c < N) xj[c] = v[e];
   }
   ai = r.ni;
-  if (lane == 0) *nj = r.nj;
+  wi *= r.c2;
+  if (lane == 0) *nj = make_double2(r.nj, sj.y * r.c2);
   TCB_T(t4);
   TCB_ACC(2, t2, t3);
   TCB_ACC(3, t3, t4);
@@ -253,8 +263,8 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
   cplx *const sP = reinterpret_cast<cplx *>(smem_raw);
   cplx *const sQ = sP + (size_t)BR * N;  // Q[buf] = sQ + buf * BR * N
   unsigned char *const tail = smem_raw + (size_t)3 * BR * d.n2 * sizeof(cplx);
-  double *const s_nrm2 = reinterpret_cast<double *>(tail);
-  uint64_t *const barP = reinterpret_cast<uint64_t *>(tail + d.n2 * sizeof(double));
+  double2 *const s_nrm2 = reinterpret_cast<double2 *>(tail);  // per row: {true squared norm, squared scale w}
+  uint64_t *const barP = reinterpret_cast<uint64_t *>(tail + d.n2 * sizeof(double2));
   uint64_t *const barQ = barP + 1;
   int *const s_ver = reinterpret_cast<int *>(barP + 4);
   const int tid = threadIdx.x, lane = tid & 31, warp = __reduce_max_sync(0xffffffffu, tid >> 5);  // provably uniform
@@ -282,13 +292,13 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
       double s = 0.0;
       for (int c = lane; c < N; c += 32) s += cabs2(__ldcg(reinterpret_cast<const double2 *>(row + c)));
       s = tcj::warp_sum(s);
-      if (lane == 0) s_nrm2[r] = s;
+      if (lane == 0) s_nrm2[r] = make_double2(s, 1.0);  // every row was folded when its block left the P stage
     }
     if (tid == 0) *s_rot = 0;
     __syncthreads();
     if (sweep == 0) {
       double p = 0.0;
-      for (int r = tid; r < K; r += NT) p += s_nrm2[r];
+      for (int r = tid; r < K; r += NT) p += s_nrm2[r].x;
       dead = tcj::DEAD_REL2 * block_sum(p, red);
     }
     // threshold Jacobi: the early sweeps rotate only the pairs that are far from orthogonal (|g|^2 / (a_i a_j) above
@@ -338,7 +348,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
         const int wl = warp - half * (BR / 2);
         const int rowsB = half ? rowsN : rowsP;
         cplx *blk = half ? sQ : sP;
-        double *nb = s_nrm2 + (p + half) * BR;
+        double2 *nb = s_nrm2 + (p + half) * BR;
         const int rmax = max(rowsP, rowsN) - 1;
         for (int r = 0; r < rmax; ++r) {
           if (r < rowsB - 1 && wl < rowsB / 2) {
@@ -360,7 +370,9 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
         const int c = lane + 32 * e;
         u[e] = (haveP && (FULL || c < N)) ? sP[(size_t)warp * N + c] : cmake(0.0, 0.0);
       }
-      double aP = haveP ? s_nrm2[p * BR + warp] : 0.0;  // squared norm of the stationary row, in a register for the visits
+      // squared norm and squared scale of the stationary row, in registers for the visits
+      const double2 sP0 = haveP ? s_nrm2[p * BR + warp] : make_double2(0.0, 1.0);
+      double aP = sP0.x, wP = sP0.y;
       // ---- every later block streams through Q
       for (int q = p + 1; q < nblk; ++q) {
         const int buf = (q - p - 1) & 1;
@@ -392,7 +404,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
             if (s == BR / 2) prefetch_next();
             const int jq = (warp + s) & (BR - 1);
             if (haveP && jq < rowsQ)
-              nrot += pair_reg<NPL, FULL>(u, Q + (size_t)jq * N, N, lane, aP, s_nrm2 + q * BR + jq, dead, tol2, small2
+              nrot += pair_reg<NPL, FULL>(u, Q + (size_t)jq * N, N, lane, aP, wP, s_nrm2 + q * BR + jq, dead, tol2, small2
 #ifdef TCB_TIMING
                                           , tacc
 #endif
@@ -424,7 +436,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
             TCB_T(tw1);
             TCB_ACC(4, tw0, tw1);
             if (haveP && jq < rowsQ)
-              nrot += pair_reg<NPL, FULL>(u, Q + (size_t)jq * N, N, lane, aP, s_nrm2 + q * BR + jq, dead, tol2, small2
+              nrot += pair_reg<NPL, FULL>(u, Q + (size_t)jq * N, N, lane, aP, wP, s_nrm2 + q * BR + jq, dead, tol2, small2
 #ifdef TCB_TIMING
                                           , tacc
 #endif
@@ -449,11 +461,13 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
       TCC_T(c9);
       // ---- block p back to global
       if (haveP) {
-        if (lane == 0) s_nrm2[p * BR + warp] = aP;
+        // the row's scale goes back into its elements here, once per sweep (every block is the P block once)
+        const double sc = sqrt(wP);
+        if (lane == 0) s_nrm2[p * BR + warp] = make_double2(aP, 1.0);
 #pragma unroll
         for (int e = 0; e < NPL; ++e) {
           const int c = lane + 32 * e;
-          if (FULL || c < N) sP[(size_t)warp * N + c] = u[e];
+          if (FULL || c < N) sP[(size_t)warp * N + c] = cscale(u[e], sc);
         }
       }
       fence_async_smem();
@@ -498,7 +512,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
   }
 }
 
-// dynamic smem: 3 * BR * n2 cplx (P, Q0, Q1) + n2 doubles + 3 mbarriers (n2 <= MAX_N).
+// dynamic smem: 3 * BR * n2 cplx (P, Q0, Q1) + n2 double2 + 3 mbarriers (n2 <= MAX_N).
 // MAXNPL = 8: any matrix up to 256 columns, one CTA per SM (128 registers).  MAXNPL = 4: contexts whose widest matrix
 // has 128 columns (chi_cap <= 64: BASELINE configs 2 and 3) -- rows are half as long, 64 registers and 98 KB of shared
 // memory are enough, and two CTAs per SM hide each other's latency chains.
@@ -513,7 +527,7 @@ __global__ void __launch_bounds__(NT, MAXNPL <= 4 ? 2 * CTAS_PER_SM : CTAS_PER_S
   const int N = __reduce_max_sync(0xffffffffu, b.N), K = __reduce_max_sync(0xffffffffu, b.M < b.N ? b.M : b.N);
   cplx *X = d.Xw + b.slot * d.slot_stride;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)3 * BR * d.n2 * sizeof(cplx) + d.n2 * sizeof(double));
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)3 * BR * d.n2 * sizeof(cplx) + d.n2 * sizeof(double2));
   __shared__ double red[32];
   __shared__ int s_rot;
   if (threadIdx.x == 0) {
