@@ -87,9 +87,16 @@ def test_headline_shape_against_oracle(engine):
     _compare(name, out, _oracle(name))
 
 
-def test_wide_matrices_truncated_against_oracle(engine):
-    """chi_max = 256 binding (theta 512 x 512: the wide QR instance and the cluster Jacobi kernel, BASELINE config 4's
-    regime) at L = 18, where an untruncated bond would reach 512."""
+@pytest.mark.parametrize('cluster', ['auto', '1', '2', '8', 'wide_v1'])
+def test_wide_matrices_truncated_against_oracle(engine, cluster, monkeypatch):
+    """chi_max = 256 binding (theta 512 x 512: the wide QR instance and the team Jacobi kernel on a thread-block
+    cluster, BASELINE config 4's regime) at L = 18, where an untruncated bond would reach 512.  The cluster size
+    (TC_WIDE_CLUSTER: CTAs per matrix; automatic = as many as fill the GPU) changes the pair order, not the result;
+    wide_v1 is the warp-per-pair cluster kernel of round 1."""
+    if cluster == 'wide_v1':
+        monkeypatch.setenv('TC_JACOBI', 'wide_v1')
+    elif cluster != 'auto':
+        monkeypatch.setenv('TC_WIDE_CLUSTER', cluster)
     name = 'wide_L18_chi256'
     out = _gpu_schedule(name)
     assert out['chi'].max() == 256
@@ -178,3 +185,52 @@ def test_svd_shortcuts_change_nothing_at_rounding_level(engine, switch, monkeypa
         assert np.max(np.abs(sa - sb) / sa) < 1e-10
     base.close()
     other.close()
+
+
+@pytest.mark.parametrize('L,chi,prep,variants', [
+    (16, 128, 9, ['TC_JACOBI=blocked', 'TC_JACOBI=team']),
+    (18, 256, 10, ['TC_WIDE_CLUSTER=1', 'TC_WIDE_CLUSTER=4', 'TC_WIDE_CLUSTER=8', 'TC_JACOBI=wide_v1']),
+])
+def test_svd_kernels_repeatedly_against_lapack(engine, L, chi, prep, variants, monkeypatch):
+    """Stress test of the batched SVD stage on its own: both parity layers applied 12 times from the same saturated
+    state with every Jacobi kernel variant; the singular values the kernel leaves (row norms of the workspace) must be
+    LAPACK's of theta = diag(S_i x 1_2) C every time, to 1e-12 of the largest.  (A race between the two warps of a
+    team left half a row unscaled in about one run in five of the first version of the team kernel; the 1e-8
+    comparisons on observables see that only when it hits a well-populated Schmidt value.)"""
+    from time_crystal_tensor_network_b200 import engine as eng
+    from time_crystal_tensor_network_b200 import _lib
+    monkeypatch.setenv('TC_GROUPS', '1')
+    hs = np.array([eng.disorder_fields(L, 0.3, 11)])
+    kw = dict(epsilon=0.3, chi_max=chi, mode='tebd', svd_min=1e-12, trunc_cut=1e-7)
+    base = eng.FloquetEnsemble(L, 1.0, 1.0, hs, **kw)
+    base.ctx.floquet_step(prep)
+    base.ctx.sync()
+    chi0 = base.ctx.chi()[0]
+    assert chi0.max() == chi
+    for var in variants:
+        key, val = var.split('=')
+        monkeypatch.setenv(key, val)
+        e = eng.FloquetEnsemble(L, 1.0, 1.0, hs, **kw)
+        monkeypatch.delenv(key)
+        for parity in (0, 1):
+            sv = {}
+            for rep in range(12):
+                e.ctx._arena.copy_(base.ctx._arena)
+                e.ctx.apply_layer(parity, 0)
+                e.ctx.sync()
+                for jb in range(L // 2):
+                    i = 2 * jb + parity
+                    if i + 1 >= L:
+                        continue
+                    M, N = 2 * int(chi0[i]), 2 * int(chi0[i + 2])
+                    if min(M, N) < 64:
+                        continue
+                    if rep == 0:
+                        C = e.ctx.dbg_get(_lib.DBG_C, 0, jb, (M, N), np.complex128)
+                        sv[jb] = np.linalg.svd(C * np.repeat(base.ctx.get_S(0, i), 2)[:, None], compute_uv=False)
+                    w = np.sort(e.ctx.dbg_get(_lib.DBG_W, 0, jb, (min(M, N),), np.float64))[::-1]
+                    err = np.max(np.abs(w - sv[jb])) / sv[jb][0]
+                    assert err < 1e-12, (var, parity, rep, jb, M, N, err)
+        assert e.ctx.flags()['svd_not_converged'] == 0
+        e.close()
+    base.close()

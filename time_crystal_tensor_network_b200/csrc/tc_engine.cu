@@ -24,6 +24,7 @@
 #include "tc_gemm.cuh"
 #include "tc_jacobi.cuh"
 #include "tc_jacobi_blocked.cuh"
+#include "tc_jacobi_team.cuh"
 #include "tc_observe.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -66,6 +67,9 @@ struct tc_ctx {
   bool no_small_kernel = false;  // TC_SMALL_KERNEL=0: the 128-register Jacobi kernel for narrow contexts too (A/B)
   bool qrw_attr_set = false, qr_attr_set = false;
   bool force_simple_jacobi = false;  // TC_JACOBI=simple: the warp-per-pair kernel for every size (A/B testing)
+  bool team_jacobi = false;          // TC_JACOBI=team: the two-warps-per-row kernel for the narrow matrices too (A/B testing)
+  bool team_attr_set = false;
+  bool old_wide = false;             // TC_JACOBI=wide_v1: the warp-per-pair cluster kernel for chi_cap > 128 (A/B testing)
   // chain groups: the chains never interact, so G groups run their periods on G streams and the tail of one group's
   // layer (fewer CTAs than SMs left) overlaps the next kernels of the others.  TC_GROUPS, default 4.
   int ngroups = 1;
@@ -390,7 +394,41 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
     }
     {
       ProfScope ps(c, TC_PROF_JACOBI);
-      if (d.n2 <= tcb::MAX_N && !c->force_simple_jacobi) {
+      auto launch_team = [&](int maxnpl) -> int {
+        // a cluster of CS CTAs per matrix when the launch has too few matrices to fill the GPU
+        const int per_sm = maxnpl <= 4 ? 2 : 1;
+        int CS = 1;
+        while (CS < 8 && (long long)nb * nr * CS * 2 <= (long long)c->sm_count * per_sm) CS *= 2;
+        if (c->wide_cluster > 0) CS = c->wide_cluster;
+        const size_t smem = tct::smem_bytes(d.n2);
+        if (!c->team_attr_set) {
+          CK(cudaFuncSetAttribute(tct::jacobi_team_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tct::smem_bytes(512)));
+          CK(cudaFuncSetAttribute(tct::jacobi_team_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tct::smem_bytes(256)));
+          c->team_attr_set = true;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(nb * CS, nr);
+        cfg.blockDim = dim3(tct::NT);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CS;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (maxnpl <= 4)
+          CK(cudaLaunchKernelEx(&cfg, tct::jacobi_team_kernel<4>, d, a, CS));
+        else
+          CK(cudaLaunchKernelEx(&cfg, tct::jacobi_team_kernel<8>, d, a, CS));
+        return 0;
+      };
+      if (d.n2 <= tcb::MAX_N && c->team_jacobi) {
+        if (launch_team(4)) return 1;
+      } else if (d.n2 > tcb::MAX_N && d.n2 <= 512 && !c->force_simple_jacobi && !c->old_wide) {
+        if (launch_team(8)) return 1;
+      } else if (d.n2 <= tcb::MAX_N && !c->force_simple_jacobi) {
         const size_t smem = (size_t)3 * tcb::BR * d.n2 * sizeof(cplx) + d.n2 * sizeof(double2) + 64 + 2 * tcb::BR * sizeof(int);
         if (!c->blocked_attr_set) {
           CK(cudaFuncSetAttribute(tcb::jacobi_blocked_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -617,6 +655,8 @@ int tc_ctx_create2(int device, int L, int chi_cap, int R, int storage_only, void
   if (const char *e = getenv("TC_GROUPS")) c->ngroups = atoi(e) > 0 ? atoi(e) : 1;
   if (const char *e = getenv("TC_JACOBI")) {
     c->force_simple_jacobi = strcmp(e, "simple") == 0;
+    c->team_jacobi = strcmp(e, "team") == 0;
+    c->old_wide = strcmp(e, "wide_v1") == 0;
   }
   if (stream) {
     c->stream = (cudaStream_t)stream;
