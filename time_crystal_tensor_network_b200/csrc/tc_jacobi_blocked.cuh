@@ -292,7 +292,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
       double s = 0.0;
       for (int c = lane; c < N; c += 32) s += cabs2(__ldcg(reinterpret_cast<const double2 *>(row + c)));
       s = tcj::warp_sum(s);
-      if (lane == 0) s_nrm2[r] = make_double2(s, 1.0);  // every row was folded during the previous sweep
+      if (lane == 0) s_nrm2[r] = make_double2(s, 1.0);  // every row was folded when its block left the P stage
     }
     if (tid == 0) *s_rot = 0;
     __syncthreads();
@@ -313,12 +313,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
     int nrot = 0;
     TCC_T(c1);
     TCC_ACC(0, c0, c1);
-    // The internal pairs of two neighbouring blocks are rotated side by side, the blocks paired from the END
-    // ((nblk-2, nblk-1), (nblk-4, nblk-3), ...; block 0 is on its own when nblk is odd): the last block then gets its
-    // internal pairs and its only visit in the pass of block nblk-2, has its scales folded there and needs no pass of
-    // its own (one load and one store of a block less per sweep).
-    const int npass = nblk > 1 ? nblk - 1 : 1;
-    for (int p = 0; p < npass; ++p) {
+    for (int p = 0; p < nblk; ++p) {
       TCC_T(c2);
       const int rowsP = min(BR, K - p * BR);
       cplx *gP = X + (size_t)p * BR * N;
@@ -341,8 +336,8 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
       // prefetched into stage 0, on warps BR/2..BR-1) so that no warp idles; any order of the pairs within a
       // sweep is a valid cyclic Jacobi ordering.
       bool q0_ready = false;
-      const bool pairUp = ((nblk - 1 - p) & 1) != 0;  // implies p + 1 < nblk
-      if (pairUp || p == 0) {
+      if ((p & 1) == 0) {
+        const bool pairUp = p + 1 < nblk;
         const int rowsN = pairUp ? min(BR, K - (p + 1) * BR) : 0;
         if (pairUp) {
           mbar_wait(&barQ[0], phQ0);
@@ -457,17 +452,6 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
         }
         TCC_T(c7);
         TCC_ACC(4, c6, c7);
-        if (p == nblk - 2) {
-          // q = nblk - 1 is visited for the last time in this sweep and has no pass of its own: its rows' scales go
-          // back into their elements here
-          __syncthreads();
-          for (int r = warp; r < rowsQ; r += NW) {
-            const double sc = sqrt(s_nrm2[q * BR + r].y);
-            for (int c = lane; c < N; c += 32) Q[(size_t)r * N + c] = cscale(Q[(size_t)r * N + c], sc);
-          }
-          __syncthreads();
-          for (int r = tid; r < rowsQ; r += NT) s_nrm2[q * BR + r].y = 1.0;
-        }
         fence_async_smem();
         __syncthreads();
         if (tid == 0) bulk_store(X + (size_t)q * BR * N, Q, rowsQ * row_bytes);
@@ -477,8 +461,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
       TCC_T(c9);
       // ---- block p back to global
       if (haveP) {
-        // the row's scale goes back into its elements here, once per sweep (every block but the last is the P block
-        // once; the last block is folded in its last visit)
+        // the row's scale goes back into its elements here, once per sweep (every block is the P block once)
         const double sc = sqrt(wP);
         if (lane == 0) s_nrm2[p * BR + warp] = make_double2(aP, 1.0);
 #pragma unroll
