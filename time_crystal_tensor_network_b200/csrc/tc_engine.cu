@@ -22,6 +22,7 @@
 #include "../../include/tc_b200.h"
 #include "tc_common.cuh"
 #include "tc_gemm.cuh"
+#include "tc_theta.cuh"
 #include "tc_jacobi.cuh"
 #include "tc_jacobi_blocked.cuh"
 #include "tc_jacobi_team.cuh"
@@ -67,6 +68,7 @@ struct tc_ctx {
   bool no_small_kernel = false;  // TC_SMALL_KERNEL=0: the 128-register Jacobi kernel for narrow contexts too (A/B)
   bool qrw_attr_set = false, qr_attr_set = false;
   bool force_simple_jacobi = false;  // TC_JACOBI=simple: the warp-per-pair kernel for every size (A/B testing)
+  bool old_theta = false;            // TC_THETA=v1: the policy-functor GEMM of round 1 for K1 (A/B testing)
   bool team_jacobi = false;          // TC_JACOBI=team: the two-warps-per-row kernel for the narrow matrices too (A/B testing)
   bool team_attr_set = false;
   bool old_wide = false;             // TC_JACOBI=wide_v1: the warp-per-pair cluster kernel for chi_cap > 128 (A/B testing)
@@ -363,7 +365,12 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
     LayerArgs a{first_site, 2, nb, r0, nr, kick_mode, gate_override, diag, ws_lo};
     {
       ProfScope ps(c, TC_PROF_THETA);
-      tcg::gemm_kernel<ThetaPolicy><<<dim3(tiles, nb, nr), tcg::NT, 0, st>>>(d, a);
+      if (c->old_theta) {
+        tcg::gemm_kernel<ThetaPolicy><<<dim3(tiles, nb, nr), tcg::NT, 0, st>>>(d, a);
+      } else {
+        const int tm = (d.n2 + tch::BM - 1) / tch::BM, tn = (d.chi_cap + tch::BNB - 1) / tch::BNB;
+        tch::theta_gemm_kernel<<<dim3(tm * tn, nb, nr), tch::NT, 0, st>>>(d, a);
+      }
       LAUNCHED();
       if (!diag) {
         const int gx = (d.chi_cap * d.chi_cap + 255) / 256;
@@ -652,6 +659,7 @@ int tc_ctx_create2(int device, int L, int chi_cap, int R, int storage_only, void
   if (const char *e = getenv("TC_SMALL_KERNEL")) c->no_small_kernel = atoi(e) == 0;
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
   if (const char *e = getenv("TC_WIDE_CLUSTER")) c->wide_cluster = atoi(e);
+  if (const char *e = getenv("TC_THETA")) c->old_theta = strcmp(e, "v1") == 0;
   if (const char *e = getenv("TC_GROUPS")) c->ngroups = atoi(e) > 0 ? atoi(e) : 1;
   if (const char *e = getenv("TC_JACOBI")) {
     c->force_simple_jacobi = strcmp(e, "simple") == 0;
