@@ -2,7 +2,12 @@
 (wall time, throughput, bond dimensions, a physics fingerprint).  These are completeness runs, not bench lines
 (bench.py measures the headline metric); the parity of every code path they use is in tests/.
 
-    python scripts/run_baseline_configs.py [2 3 4 5] [--quick]
+    python scripts/run_baseline_configs.py [2 3 4 5] [--quick] [--cpu]
+
+Every ensemble line carries the algorithmic FP64 work of the run (SURVEY 8d flop model on the recorded bond dimensions)
+as TFLOP/s and as a fraction of the FP64 peak measured in the same process (tc_probe_fp64).  With --cpu the final state
+of chain 0 is handed to the CPU oracle (oracle/tebd_ref.py, the checker: one single-threaded process), which evolves it
+one more period; the GPU evolves the same period, the two are compared (max |delta| of <Z_i>, entropies) and timed.
 """
 import json
 import sys
@@ -13,7 +18,54 @@ import numpy as np
 sys.path.insert(0, '.')
 from time_crystal_tensor_network_b200 import engine as eng  # noqa: E402
 
+import bench  # noqa: E402  (flop model)
+
 QUICK = '--quick' in sys.argv
+CPU = '--cpu' in sys.argv
+PEAK = None
+
+
+def fp64_peak():
+    global PEAK
+    if PEAK is None:
+        PEAK = eng.probe_fp64(0, False) * 1e-3
+    return PEAK
+
+
+def run_flops(chi_rec, periods):
+    """Algorithmic flop of a run from its bond-dimension records chi_rec[T][R][L+1] (T records spread evenly over
+    `periods` periods): trapezoid over the records of the per-period count of bench.update_flops."""
+    T = chi_rec.shape[0]
+    per = np.array([sum(sum(bench.update_flops(chi_rec[t, r])) for r in range(chi_rec.shape[1])) for t in range(T)])
+    if T == 1:
+        return float(per[0] * periods)
+    return float(np.sum(0.5 * (per[1:] + per[:-1])) * periods / (T - 1))
+
+
+def cpu_check(ens, L, chi, eps):
+    """One more period of chain 0 on the GPU and on the CPU oracle from the same state."""
+    from oracle import tebd_ref   # checker and CPU baseline only
+    ctx = ens.ctx
+    Bs = [ctx.get_site(0, i) for i in range(L)]
+    Ss = [ctx.get_S(0, b) for b in range(L + 1)]
+    psi = tebd_ref.MPS([None] * L, Bs, Ss, [(0.0, 1.0)] * L)
+    kick = np.asarray(ens.kick[0])
+    gates = [ens.gates[0, i] for i in range(L - 1)]
+    trunc = dict(chi_max=chi, svd_min=1e-12, trunc_cut=1e-7)
+    t0 = time.time()
+    psi2, _ = tebd_ref.floquet_step(psi, kick, gates, mode='tebd', trunc=trunc)
+    t_cpu = time.time() - t0
+    t0 = time.time()
+    ctx.floquet_step(1)
+    ctx.sync()
+    t_gpu = time.time() - t0
+    rdm, ent = ctx.measure()
+    z = rdm[0, :, 0] - rdm[0, :, 1]
+    return {'cpu_oracle_s_per_period_chain0': round(t_cpu, 3), 'gpu_s_per_period_whole_ensemble': round(t_gpu, 4),
+            'max_abs_dZ': float(np.max(np.abs(z - tebd_ref.site_z(psi2)))),
+            'max_abs_dS': float(np.max(np.abs(ent[0] - psi2.entanglement_entropy()))),
+            'chi_equal': bool(list(ctx.chi()[0][1:-1]) == list(psi2.chi))}
+
 WHICH = [int(a) for a in sys.argv[1:] if a.isdigit()] or [1, 2, 3, 4, 5]
 
 
@@ -40,6 +92,13 @@ def run_ensemble(tag, L, chi, hs, eps, n_periods, measure_every=1, **kw):
            'chain_steps_per_s': round(R * n_periods / dt, 1), 'chi_reached': int(out['chi'].max()),
            'S_mid_final_mean': float(out['S_ent'][-1][:, L // 2 - 1].mean()),
            'LE_final_mean': float(out['LE'][-1].mean()), 'flags': {k: float(v) for k, v in out['flags'].items()}}
+    fl = run_flops(out['chi'], n_periods)
+    res['algorithmic_tflop'] = round(fl * 1e-12, 3)
+    res['tflops'] = round(fl / run_s * 1e-12, 3) if run_s > 0 else None
+    res['frac_of_fp64_peak'] = round(fl / run_s * 1e-12 / fp64_peak(), 4) if run_s > 0 else None
+    res['fp64_peak_tflops'] = round(fp64_peak(), 2)
+    if CPU and chi > 1 and out['chi'].max() > 1:
+        res['cpu_check'] = cpu_check(ens, L, chi, eps)
     ens.close()
     return res, out, stag
 
