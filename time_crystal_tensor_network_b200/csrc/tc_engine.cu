@@ -63,6 +63,9 @@ struct tc_ctx {
   cplx *op_scratch = nullptr;                      // 32 cplx: caller-supplied operators
   cplx *E0 = nullptr, *E1 = nullptr, *Tt = nullptr;  // transfer contraction scratch
   double *small_out = nullptr;                       // 8 doubles
+  cplx *ovs = nullptr;                               // [R][2][chi_cap] half vectors of overlap_product_kernel
+  int *ovc = nullptr;                                // [R] arrival counters of its two CTAs per chain
+  bool ov_attr_set = false;
   bool have_model = false;
   bool blocked_attr_set = false;
   bool no_small_kernel = false;  // TC_SMALL_KERNEL=0: the 128-register Jacobi kernel for narrow contexts too (A/B)
@@ -127,7 +130,7 @@ static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct Layout {
   size_t B, S, chi, init_idx, gates, kick, trunc_err, flags, Cw, Xw, ww, perm, knew, renorm, op, E0, E1, Tt,
-      small_out, total;
+      small_out, ovs, ovc, total;
   int ws_chains, nbmax, n2;
 };
 
@@ -171,6 +174,8 @@ static Layout make_layout(int L, int chi_cap, int R, bool storage_only = false) 
   o.E1 = take((size_t)chi_cap * chi_cap * cs);
   o.Tt = take((size_t)chi_cap * 2 * chi_cap * cs);
   o.small_out = take(8 * sizeof(double));
+  o.ovs = take((size_t)R * 2 * chi_cap * cs);  // half vectors of the product-state overlap
+  o.ovc = take((size_t)R * sizeof(int));
   o.total = p;
   return o;
 }
@@ -590,7 +595,14 @@ static int measure_range(tc_ctx *c, double *rdm, double *Z, double *ent, double 
     LAUNCHED();
   }
   if (ov) {
-    tco::overlap_product_kernel<<<nr, tco::NT, (2 * d.chi_cap + (tco::NT / 32) * tco::OVC) * sizeof(cplx), st>>>(d, r_lo, ov);
+    // (running this latency-bound chain on a side stream next to the bandwidth-bound measure kernel was measured:
+    // 0.170 -> 0.167 ms per snapshot, not worth the extra streams and events)
+    const size_t smem = (2 * (size_t)d.chi_cap + (tco::NT_OV / 32) * tco::OVC) * sizeof(cplx);
+    if (!c->ov_attr_set) {
+      CK(cudaFuncSetAttribute(tco::overlap_product_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      c->ov_attr_set = true;
+    }
+    tco::overlap_product_kernel<<<dim3(nr, 2), tco::NT_OV, smem, st>>>(d, r_lo, ov, c->ovs, c->ovc);
     LAUNCHED();
   }
   if (chi) {
@@ -723,6 +735,9 @@ int tc_ctx_create2(int device, int L, int chi_cap, int R, int storage_only, void
   c->E1 = (cplx *)(base + lo.E1);
   c->Tt = (cplx *)(base + lo.Tt);
   c->small_out = (double *)(base + lo.small_out);
+  c->ovs = (cplx *)(base + lo.ovs);
+  c->ovc = (int *)(base + lo.ovc);
+  cudaMemsetAsync(c->ovc, 0, (size_t)R * sizeof(int), c->stream);
   d.mode = TC_TRUNC_REFERENCE;
   d.cutoff = 1e-13;
   d.chi_max = 0;

@@ -158,9 +158,16 @@ __device__ __forceinline__ void tcg_dmma(double &c0, double &c1, double a, doubl
 
 constexpr int QNT = 256, QMAXM = 256;    // fast-path instance: M <= 256 rows, 256 threads
 constexpr int QNTW = 512, QMAXMW = 512;  // wide instance (chi_cap <= 256): M <= 512 rows, 512 threads
+#ifndef TC_QR_U1
+#define TC_QR_U1 4  // rows-of-4 steps of pass 1 of the trailing update in flight per warp
+#endif
+#ifndef TC_QR_U2
+#define TC_QR_U2 2  // rows-of-8 steps of pass 2 in flight per warp
+#endif
 #ifndef TC_QB
 #define TC_QB 8
 #endif
+constexpr int QRU1 = TC_QR_U1, QRU2 = TC_QR_U2;
 constexpr int QBDEF = TC_QB;  // panel width (8 or 16 columns).  16 halves the passes over the trailing matrix but was measured
                               // slower on the B200 (QR share of the step 6.9 % -> 10.0 %, r02d): the kernel is bound by the panel
                               // factorisation (block reductions, V^H V, T) and not by the trailing update
@@ -315,7 +322,7 @@ __global__ void __launch_bounds__(QT) qr_blocked_kernel(TcDev d, LayerArgs a) {
         double wre[MT][2], wim[MT][2];
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) wre[mt][0] = wre[mt][1] = wim[mt][0] = wim[mt][1] = 0.0;
-#pragma unroll 4
+#pragma unroll QRU1
         for (int r0 = 0; r0 < rows; r0 += 4) {
           const int r = r0 + fk;
           const bool rok = r < rows;
@@ -348,7 +355,7 @@ __global__ void __launch_bounds__(QT) qr_blocked_kernel(TcDev d, LayerArgs a) {
         }
         __syncwarp();
         const int cc = c0 + 2 * fk;
-#pragma unroll 2
+#pragma unroll QRU2
         for (int r0 = 0; r0 < rows; r0 += 8) {
           const int r = r0 + fr;
           const bool rok = r < rows;

@@ -98,61 +98,151 @@ __global__ void __launch_bounds__(NT) measure_kernel(TcDev d, int r0, double *rd
   }
 }
 
-// <psi0|psi> for the product state psi0 given to tc_set_product_state: one CTA per chain, a chain
-// of vector-matrix products v <- v B_i[:, idx_i, :].  The sites are inherently sequential; inside a site the rows of
-// the slice are dealt to the warps (warp w takes rows w, w+8, ...: every row is one coalesced read of chi_r complex,
-// four rows in flight per warp), each lane accumulates its columns, and the 8 partial vectors are added through
-// shared memory.  (Thread per column with a serial loop over the rows left half the CTA idle and one load in flight
-// per thread: 0.50 ms per snapshot at the metric shape.)
-// dynamic smem: (2 chi_cap + 8 OVC) cplx
-constexpr int OVC = 128;  // columns per pass
-__global__ void __launch_bounds__(NT) overlap_product_kernel(TcDev d, int r0, double *ov) {
-  const int r = r0 + blockIdx.x;
+// <psi0|psi> for the product state psi0 given to tc_set_product_state (reference op: MPS.overlap behind
+// calculate_loschmidt_echo, src/core/observables.py:11-38): the contraction is a chain of (chi_l x chi_r) slices
+// M_i = B_i[:, idx_i, :] of the site tensors, <psi0|psi> = e^T M_0 M_1 ... M_{L-1} e.  The chain is cut in the middle
+// and the two halves run as TWO CTAs per chain: blockIdx.y = 0 carries a row vector from the left end (v <- v M_i),
+// blockIdx.y = 1 a column vector from the right end (w <- M_i w); whichever CTA finishes second (a counter per chain)
+// forms v . w.  32 warps per CTA so that every row of a 128-row slice is in flight at once: a site costs one round trip
+// to memory instead of four.
+//   left half:  warp w takes rows w, w + 32, ...; every lane accumulates its columns, the 32 partial vectors are added
+//               through shared memory (two levels);
+//   right half: warp w takes rows w, w + 32, ...; a row is one dot product with w (coalesced read, warp reduction).
+// scratch: ovs[R][2][chi_cap] complex (the two half vectors), ovc[R] arrival counters (left at zero for the next call).
+// dynamic smem: (2 chi_cap + 32 * OVC) cplx
+constexpr int OVC = 128;    // columns per pass of the left half
+constexpr int NT_OV = 1024;
+// the slice of site i (chi_l rows of chi_r complex, row a at (2 a + idx) chi_r) into L2 ahead of its use: the loads of a
+// site do not depend on the vector, only the FMAs do, so the next site's lines travel while this site is reduced
+__device__ __forceinline__ void ov_prefetch(const cplx *B, int chiL, int chiR, int tid) {
+  const int lines_per_row = (chiR * (int)sizeof(cplx) + 127) / 128;
+  for (int e = tid; e < chiL * lines_per_row; e += 1024) {
+    const int a2 = e / lines_per_row, l = e - a2 * lines_per_row;
+    const char *p = reinterpret_cast<const char *>(B + (size_t)(2 * a2) * chiR) + 128 * l;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+  }
+}
+
+__global__ void __launch_bounds__(NT_OV) overlap_product_kernel(TcDev d, int r0, double *ov, cplx *ovs, int *ovc) {
+  const int r = r0 + blockIdx.x, dir = blockIdx.y;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx *v = reinterpret_cast<cplx *>(smem_raw);
   cplx *vn = v + d.chi_cap;
-  cplx *part = vn + d.chi_cap;  // [NT / 32][OVC]
-  const int *c = d.chi + (size_t)r * (d.L + 1);
+  cplx *part = vn + d.chi_cap;  // [32][OVC]
+  __shared__ int s_chi[1026];
+  __shared__ int8_t s_idx[1025];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = NT / 32;
+  constexpr int NW = NT_OV / 32;
+  const int L = d.L, Lh = L / 2;  // the left half covers sites 0 .. Lh-1, the right half sites Lh .. L-1
+  // bond dimensions and basis indices of the chain into shared memory once (the slice addresses depend on them: two
+  // dependent global loads per site otherwise); chains longer than 1024 sites read them from global memory
+  const bool cached = L <= 1024;
+  const int *c = d.chi + (size_t)r * (L + 1);
+  if (cached) {
+    for (int k = tid; k <= L; k += NT_OV) s_chi[k] = c[k];
+    for (int k = tid; k < L; k += NT_OV) s_idx[k] = d.init_idx[(size_t)r * L + k];
+  }
   if (tid == 0) v[0] = cmake(1.0, 0.0);
   __syncthreads();
-  for (int i = 0; i < d.L; ++i) {
-    const int chiL = c[i], chiR = c[i + 1];
-    const int idx = d.init_idx[(size_t)r * d.L + i];
-    const cplx *B = site_ptr(d, r, i) + (size_t)idx * chiR;
-    for (int c0 = 0; c0 < chiR; c0 += OVC) {
-      cplx acc[OVC / 32];
+  if (dir == 0) {
+    for (int i = 0; i < Lh; ++i) {
+      const int chiL = cached ? s_chi[i] : c[i], chiR = cached ? s_chi[i + 1] : c[i + 1];
+      const int idx = cached ? s_idx[i] : d.init_idx[(size_t)r * L + i];
+      const cplx *B = site_ptr(d, r, i) + (size_t)idx * chiR;
+      for (int j = (i == 0 ? 1 : 2); cached && j <= 2 && i + j < Lh; ++j)  // two sites ahead (site 1 too at the start)
+        ov_prefetch(site_ptr(d, r, i + j) + (size_t)s_idx[i + j] * s_chi[i + j + 1], s_chi[i + j], s_chi[i + j + 1], tid);
+      for (int c0 = 0; c0 < chiR; c0 += OVC) {
+        cplx acc[OVC / 32];
 #pragma unroll
-      for (int k = 0; k < OVC / 32; ++k) acc[k] = cmake(0.0, 0.0);
+        for (int k = 0; k < OVC / 32; ++k) acc[k] = cmake(0.0, 0.0);
+#pragma unroll 4
+        for (int a2 = warp; a2 < chiL; a2 += NW) {
+          const cplx va = v[a2];
+          const cplx *row = B + (size_t)(2 * a2) * chiR + c0;
+#pragma unroll
+          for (int k = 0; k < OVC / 32; ++k) {
+            const int b = lane + 32 * k;
+            if (c0 + b < chiR) cfma(acc[k], va, row[b]);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < OVC / 32; ++k) part[warp * OVC + lane + 32 * k] = acc[k];
+        __syncthreads();
+        {  // 32 partial vectors -> 8 (thread t: column t % OVC, warps 4 g .. 4 g + 3 with g = t / OVC)
+          const int b = tid % OVC, g = tid / OVC;
+          cplx t = part[(4 * g) * OVC + b];
+#pragma unroll
+          for (int w = 1; w < 4; ++w) t = cadd(t, part[(4 * g + w) * OVC + b]);
+          __syncthreads();
+          part[g * OVC + b] = t;
+        }
+        __syncthreads();
+        for (int b = tid; b < OVC && c0 + b < chiR; b += NT_OV) {
+          cplx t = part[b];
+#pragma unroll
+          for (int g = 1; g < NT_OV / OVC; ++g) t = cadd(t, part[g * OVC + b]);
+          vn[c0 + b] = t;
+        }
+        __syncthreads();
+      }
+      cplx *t = v;
+      v = vn;
+      vn = t;
+    }
+  } else {
+    for (int i = L - 1; i >= Lh; --i) {
+      const int chiL = cached ? s_chi[i] : c[i], chiR = cached ? s_chi[i + 1] : c[i + 1];
+      const int idx = cached ? s_idx[i] : d.init_idx[(size_t)r * L + i];
+      const cplx *B = site_ptr(d, r, i) + (size_t)idx * chiR;
+      for (int j = (i == L - 1 ? 1 : 2); cached && j <= 2 && i - j >= Lh; ++j)
+        ov_prefetch(site_ptr(d, r, i - j) + (size_t)s_idx[i - j] * s_chi[i - j + 1], s_chi[i - j], s_chi[i - j + 1], tid);
 #pragma unroll 4
       for (int a2 = warp; a2 < chiL; a2 += NW) {
-        const cplx va = v[a2];
-        const cplx *row = B + (size_t)(2 * a2) * chiR + c0;
-#pragma unroll
-        for (int k = 0; k < OVC / 32; ++k) {
-          const int b = lane + 32 * k;
-          if (c0 + b < chiR) cfma(acc[k], va, row[b]);
+        const cplx *row = B + (size_t)(2 * a2) * chiR;
+        cplx acc = cmake(0.0, 0.0);
+        for (int b = lane; b < chiR; b += 32) cfma(acc, row[b], v[b]);
+        for (int o = 16; o > 0; o >>= 1) {
+          acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+          acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
         }
-      }
-#pragma unroll
-      for (int k = 0; k < OVC / 32; ++k) part[warp * OVC + lane + 32 * k] = acc[k];
-      __syncthreads();
-      for (int b = tid; b < OVC && c0 + b < chiR; b += NT) {
-        cplx t = part[b];
-#pragma unroll
-        for (int w = 1; w < NW; ++w) t = cadd(t, part[w * OVC + b]);
-        vn[c0 + b] = t;
+        if (lane == 0) vn[a2] = acc;
       }
       __syncthreads();
+      cplx *t = v;
+      v = vn;
+      vn = t;
     }
-    cplx *t = v;
-    v = vn;
-    vn = t;
   }
-  if (tid == 0) {
-    ov[(size_t)r * 2 + 0] = v[0].x;
-    ov[(size_t)r * 2 + 1] = v[0].y;
+  // ---- hand the half vector over; the CTA that arrives second closes the contraction
+  const int n = c[Lh];
+  cplx *mine = ovs + ((size_t)r * 2 + dir) * d.chi_cap;
+  for (int k = tid; k < n; k += NT_OV) mine[k] = v[k];
+  __threadfence();
+  __syncthreads();
+  __shared__ int s_last;
+  if (tid == 0) s_last = atomicAdd(ovc + r, 1);
+  __syncthreads();
+  if (s_last == 0) return;
+  __threadfence();
+  // both halves are read back from the scratch in a fixed order (left . right), so that the result does not depend on
+  // which CTA happens to arrive second (the records of a chain are bit-identical from run to run)
+  const cplx *left = ovs + ((size_t)r * 2 + 0) * d.chi_cap, *right = left + d.chi_cap;
+  if (warp == 0) {
+    cplx acc = cmake(0.0, 0.0);
+    for (int k = lane; k < n; k += 32) {
+      const double2 a = __ldcg(reinterpret_cast<const double2 *>(left + k));
+      const double2 b = __ldcg(reinterpret_cast<const double2 *>(right + k));
+      cfma(acc, cmake(a.x, a.y), cmake(b.x, b.y));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    }
+    if (lane == 0) {
+      ov[(size_t)r * 2 + 0] = acc.x;
+      ov[(size_t)r * 2 + 1] = acc.y;
+      ovc[r] = 0;  // ready for the next snapshot
+    }
   }
 }
 
