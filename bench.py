@@ -374,8 +374,7 @@ def run_ours(a):
         except Exception:
             peaks = {}
         value = total * a.steps / (ms_max * 1e-3)
-        cfg = make_config(a, world)
-        cfg.update({'prep_s': m['prep_s'], 'chi_mid_min': m['chi_mid_min'], 'chi_mean': m['chi_mean']})
+        cfg = make_config(a, world)      # identical, key for key, to the reference arm's `config`
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
             'ms_per_step': ms_max / a.steps, 'higher_is_better': True, 'scaling': a.scaling, 'vs_baseline': None,
@@ -409,6 +408,7 @@ def run_ours(a):
                 'chain_groups': int(os.environ.get('TC_GROUPS', 4)),
             },
             'svd_flags': m['flags'],
+            'state': {'prep_s': m['prep_s'], 'chi_mid_min': m['chi_mid_min'], 'chi_mean': m['chi_mean']},
             'gathered_Z_shape': list(Z_all.shape),
         }
         if equiv:

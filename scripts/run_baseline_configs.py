@@ -172,8 +172,10 @@ if 5 in WHICH:
     states, times, finfo = CustomFloquet(model, dict(chi_max=128, svd_min=1e-12, trunc_cut=1e-7)).evolve_floquet(gs, n_q)
     t_q = time.time() - t1
     S = np.array([s.entanglement_entropy() for s in states])
+    e_exact = -0.5 * np.sum(np.linalg.svd(2 * g * np.eye(L) - 2 * np.eye(L, k=1), compute_uv=False))   # free fermions
     emit({'config': '5: imaginary-time ground state + Floquet quench', 'L': L, 'chi_max': 128,
                     'ground_state_s': round(t_gs, 2), 'energy_per_site': float(info['energies'][-1] / L),
+                    'exact_energy_per_site': float(e_exact / L),
                     'energy_decreasing': bool(info['energies'][0] >= info['energies'][-1]),
                     'gs_max_chi': int(max(gs.chi)), 'quench_periods': n_q, 'quench_s': round(t_q, 2),
                     'S_mid_trajectory': [float(x) for x in S[:, L // 2 - 1]],
