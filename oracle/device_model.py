@@ -28,7 +28,7 @@ EPS = np.finfo(float).eps
 DEAD_REL2 = 1e-30          # rows with |x|^2 < DEAD_REL2 |theta|_F^2 are numerically zero (tc_jacobi.cuh)
 MAX_SWEEPS = 48
 SMALL_REL2 = 1e-16       # a sweep whose rotations were all below 1e-8 relative ends the iteration
-THRESHOLDS = (1e-2, 1e-3, 1e-4, 1e-6)   # tc_jacobi_blocked.cuh: sweeps 0..3 rotate only pairs with |g|^2/(a_i a_j) above
+THRESHOLDS = (3e-3, 3e-4, 3e-5, 3e-6)   # tc_engine.cu thr_sched: sweeps 0..3 rotate only pairs with |g|^2/(a_i a_j) above
 
 
 def interleave_perm(chi_r):

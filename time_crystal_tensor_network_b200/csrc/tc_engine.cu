@@ -711,7 +711,9 @@ int tc_ctx_create2(int device, int L, int chi_cap, int R, int storage_only, void
   d.rot64 = 1;  // bit 0: unused (the FP32 angle variant is gone); bit 1: lock-step rounds (barrier instead of hand-over)
   if (const char *e = getenv("TC_ROT64")) d.rot64 = atoi(e);
   {  // threshold schedule of the Jacobi sweeps 0..3; TC_THRESH=0 switches it off, TC_THRESH=a,b,c,d sets it (A/B)
-    double sched[4] = {1e-2, 1e-3, 1e-4, 1e-6};
+    // (round 1, standard rotations: 1e-2, 1e-3, 1e-4, 1e-6; re-tuned on the B200 after the fast rotations, r02 sweep in
+    // profiles/README.md: 204.6 -> 211.7 chain-steps/s, mean sweeps 8.27 -> 7.97)
+    double sched[4] = {3e-3, 3e-4, 3e-5, 3e-6};
     if (const char *e = getenv("TC_THRESH")) {
       double v[4] = {0.0, 0.0, 0.0, 0.0};
       sscanf(e, "%lf,%lf,%lf,%lf", &v[0], &v[1], &v[2], &v[3]);

@@ -302,7 +302,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
       dead = tcj::DEAD_REL2 * block_sum(p, red);
     }
     // threshold Jacobi: the early sweeps rotate only the pairs that are far from orthogonal (|g|^2 / (a_i a_j) above
-    // 1e-2, 1e-3, 1e-4, 1e-6 in sweeps 0..3); a small rotation made now is undone by the large ones around it and has
+    // 3e-3, 3e-4, 3e-5, 3e-6 in sweeps 0..3, TcDev::thr_sched); a small rotation made now is undone by the large ones around it and has
     // to be made again.  Same final accuracy and sweep count, a fifth fewer rotations (NumPy model on TEBD matrices).
     // The parameter of the pair functions called tol2 is this sweep's rotation threshold from here on.
     const double tol2 = (sweep < 4 && !thr_off) ? fmax(tol2_final, d.thr_sched[sweep]) : tol2_final;
