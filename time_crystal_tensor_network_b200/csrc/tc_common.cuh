@@ -58,7 +58,7 @@ struct TcDev {
   const cplx *kick;   // [R][4]
   int rot64;          // TC_ROT64 A/B switches of the Jacobi kernel: bit 1 = barrier per round instead of the row hand-over
   int gates_diag;     // every gate of the model is diagonal (fused phase epilogue)
-  double thr_sched[4];  // threshold Jacobi: sweeps 0..3 rotate only pairs with |g|^2 / (a_i a_j) above these
+  double thr_sched[6];  // threshold Jacobi: sweeps 0..5 rotate only pairs with |g|^2 / (a_i a_j) above these
   double small_rel2;    // stopping rule: a sweep whose rotations all had |g|^2 / (a_i a_j) below this ends the iteration
                         // (tcj::SMALL_REL2; 0 with TC_EARLY_STOP=0: iterate until a sweep rotates nothing)
   double *trunc_err;  // [R][L+1] discarded weight accumulated per bond (single writer, deterministic)

@@ -713,13 +713,13 @@ int tc_ctx_create2(int device, int L, int chi_cap, int R, int storage_only, void
   {  // threshold schedule of the Jacobi sweeps 0..3; TC_THRESH=0 switches it off, TC_THRESH=a,b,c,d sets it (A/B)
     // (round 1, standard rotations: 1e-2, 1e-3, 1e-4, 1e-6; re-tuned on the B200 after the fast rotations, r02 sweep in
     // profiles/README.md: 204.6 -> 211.7 chain-steps/s, mean sweeps 8.27 -> 7.97)
-    double sched[4] = {3e-3, 3e-4, 3e-5, 3e-6};
+    double sched[6] = {3e-3, 3e-4, 3e-5, 3e-6, 0.0, 0.0};
     if (const char *e = getenv("TC_THRESH")) {
-      double v[4] = {0.0, 0.0, 0.0, 0.0};
-      sscanf(e, "%lf,%lf,%lf,%lf", &v[0], &v[1], &v[2], &v[3]);
-      for (int k = 0; k < 4; ++k) sched[k] = v[k];
+      double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      sscanf(e, "%lf,%lf,%lf,%lf,%lf,%lf", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]);
+      for (int k = 0; k < 6; ++k) sched[k] = v[k];
     }
-    for (int k = 0; k < 4; ++k) d.thr_sched[k] = sched[k];
+    for (int k = 0; k < 6; ++k) d.thr_sched[k] = sched[k];
   }
   d.small_rel2 = tcj::SMALL_REL2;
   if (const char *e = getenv("TC_EARLY_STOP"))

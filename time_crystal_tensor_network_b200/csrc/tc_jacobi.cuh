@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(NT) jacobi_rows_cluster_kernel(TcDev d, LayerA
     }
     // threshold sweeps and their stopping rule as in tc_jacobi_blocked.cuh (here a skipped rotation also saves the
     // write-back of the two rows, half of the L2 traffic of the pair)
-    const double tol2 = sweep < 4 ? fmax(tol2_final, d.thr_sched[sweep]) : tol2_final;
+    const double tol2 = sweep < 6 ? fmax(tol2_final, d.thr_sched[sweep]) : tol2_final;
     const double small2 = tol2 > tol2_final ? tol2_final : fmax(tol2_final, d.small_rel2);
     int nrot = 0;
     for (int r = 0; r < M - 1; ++r) {

@@ -305,7 +305,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
     // 3e-3, 3e-4, 3e-5, 3e-6 in sweeps 0..3, TcDev::thr_sched); a small rotation made now is undone by the large ones around it and has
     // to be made again.  Same final accuracy and sweep count, a fifth fewer rotations (NumPy model on TEBD matrices).
     // The parameter of the pair functions called tol2 is this sweep's rotation threshold from here on.
-    const double tol2 = (sweep < 4 && !thr_off) ? fmax(tol2_final, d.thr_sched[sweep]) : tol2_final;
+    const double tol2 = (sweep < 6 && !thr_off) ? fmax(tol2_final, d.thr_sched[sweep]) : tol2_final;
     // stopping rule: a sweep that rotated every pair above the final tolerance and found them all below 1e-8 ends the
     // iteration (quadratic convergence: what is left is below 1e-16); a threshold sweep has skipped pairs, so there
     // anything above the final tolerance keeps the iteration going

@@ -331,7 +331,7 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
       for (int r = tid; r < K; r += NT) p += __ldcg(gn + r);
       dead = tcj::DEAD_REL2 * block_sum(p, red);
     }
-    const double tol2 = (sweep < 4 && !thr_off) ? fmax(tol2_final, d.thr_sched[sweep]) : tol2_final;
+    const double tol2 = (sweep < 6 && !thr_off) ? fmax(tol2_final, d.thr_sched[sweep]) : tol2_final;
     const double small2 = tol2 > tol2_final ? tol2_final : fmax(tol2_final, d.small_rel2);
     cx.nrot = 0;
     // ---- (a) all pairs inside a group: groups crank and crank + CS.  The internal pairs of two neighbouring blocks are
