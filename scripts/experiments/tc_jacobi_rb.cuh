@@ -1,3 +1,7 @@
+// NOTE (round 2): this experiment was written against the round-1 helpers of tc_jacobi_blocked.cuh (standard rotations:
+// tcb::make_rot(alive, ai, aj, gr, gi, ...), Rot{cs, sr, si, ni, nj}); the product kernel now uses fast scaled rotations with a
+// different Rot / make_rot, so this file and scripts/ubench/pair_chain.cu build only against commit 4557cd6 (round-1 final).
+// Kept for the record of the negative result (second tuning pass).
 // tc_jacobi_rb.cuh -- K2b, register-blocked variant (TC_JACOBI=rb; the 16-warp kernel of tc_jacobi_blocked.cuh is
 // the default): one-sided Jacobi on the rows of the triangular factor with FOUR stationary rows per warp in registers
 // and every streamed row reused four times per shared-memory load.

@@ -162,6 +162,21 @@ def test_bench_flop_model():
     assert ft == n * 32 * chi ** 3 and fb == n * 32 * chi ** 3 and fs == n * 672 * chi ** 3
 
 
+def test_bench_arms_share_one_config():
+    """Both arms of bench.py describe their workload with the same function; weak and strong chain counts."""
+    sys.path.insert(0, ROOT)
+    import bench
+    import argparse
+    ns = argparse.Namespace(L=32, chi=128, eps=0.1, prep_eps=0.3, prep_periods=10, chains=32, scaling='weak', total_chains=256)
+    assert bench.chains_of(ns, 8) == (32, 256)
+    cfg = bench.make_config(ns, 8)
+    assert cfg['chains_total'] == 256 and cfg['chains_per_gpu'] == 32 and cfg['seeds'] == '1000..1255'
+    ns.scaling = 'strong'
+    assert bench.chains_of(ns, 8) == (32, 256) and bench.chains_of(ns, 3) == (86, 256) and bench.chains_of(ns, 1) == (256, 256)
+    src = open(os.path.join(ROOT, 'bench.py')).read()
+    assert src.count("'config': make_config(a, world)") == 1 and src.count('cfg = make_config(a, world)') == 1   # reference arm, GPU arm
+
+
 def test_reference_import_layout():
     """With only <repo>/src on sys.path the reference's import lines work unchanged (main.py:32-37)."""
     import subprocess
