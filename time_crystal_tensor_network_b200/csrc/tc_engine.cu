@@ -65,15 +65,11 @@ struct tc_ctx {
   double *small_out = nullptr;                       // 8 doubles
   cplx *ovs = nullptr;                               // [R][2][chi_cap] half vectors of overlap_product_kernel
   int *ovc = nullptr;                                // [R] arrival counters of its two CTAs per chain
-  bool ov_attr_set = false;
   bool have_model = false;
-  bool blocked_attr_set = false;
   bool no_small_kernel = false;  // TC_SMALL_KERNEL=0: the 128-register Jacobi kernel for narrow contexts too (A/B)
-  bool qrw_attr_set = false, qr_attr_set = false;
   bool force_simple_jacobi = false;  // TC_JACOBI=simple: the warp-per-pair kernel for every size (A/B testing)
   bool old_theta = false;            // TC_THETA=v1: the policy-functor GEMM of round 1 for K1 (A/B testing)
   bool team_jacobi = false;          // TC_JACOBI=team: the two-warps-per-row kernel for the narrow matrices too (A/B testing)
-  bool team_attr_set = false;
   bool old_wide = false;             // TC_JACOBI=wide_v1: the warp-per-pair cluster kernel for chi_cap > 128 (A/B testing)
   // chain groups: the chains never interact, so G groups run their periods on G streams and the tail of one group's
   // layer (fewer CTAs than SMs left) overlaps the next kernels of the others.  TC_GROUPS, default 4.
@@ -335,6 +331,31 @@ __global__ void __launch_bounds__(256) probe_dmma_kernel(double *out, int iters)
 }
 
 // ------------------------------------------------------------------------------------------------
+// dynamic shared-memory limits of the kernels that need more than 48 KB: set once per device to the largest size any
+// context can ask for.  (The attribute is the allowed MAXIMUM and belongs to the function, not to a context: setting it
+// per context to that context's own size lets a small context lower it under a large one created earlier.)
+// ------------------------------------------------------------------------------------------------
+static constexpr size_t OV_SMEM_MAX = (2 * (size_t)1024 + (tco::NT_OV / 32) * tco::OVC) * sizeof(cplx);  // chi_cap <= 1024
+static size_t blocked_smem(int n2) {
+  return (size_t)3 * tcb::BR * n2 * sizeof(cplx) + (size_t)n2 * sizeof(double2) + 64 + 2 * tcb::BR * sizeof(int);
+}
+static int ensure_kernel_attributes(int device) {
+  static std::atomic<unsigned long long> done{0};
+  if (device < 64 && (done.load() >> device) & 1ull) return 0;
+  CK(cudaFuncSetAttribute(tcj::qr_blocked_kernel<tcj::QNT, tcj::QBDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          tcj::QNT * tcj::QBDEF * (int)sizeof(cplx)));
+  CK(cudaFuncSetAttribute(tcj::qr_blocked_kernel<tcj::QNTW, tcj::QBDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          tcj::QNTW * tcj::QBDEF * (int)sizeof(cplx)));
+  CK(cudaFuncSetAttribute(tct::jacobi_team_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tct::smem_bytes(512)));
+  CK(cudaFuncSetAttribute(tct::jacobi_team_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tct::smem_bytes(256)));
+  CK(cudaFuncSetAttribute(tcb::jacobi_blocked_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blocked_smem(tcb::MAX_N)));
+  CK(cudaFuncSetAttribute(tcb::jacobi_blocked_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blocked_smem(tcb::MAX_N)));
+  CK(cudaFuncSetAttribute(tco::overlap_product_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OV_SMEM_MAX));
+  if (device < 64) done.fetch_or(1ull << device);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // helpers
 // ------------------------------------------------------------------------------------------------
 static int check_ctx(tc_ctx *c) {
@@ -387,17 +408,9 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
       ProfScope ps(c, TC_PROF_QR);
       if (d.n2 <= tcj::QMAXM && !c->force_simple_jacobi) {
         const int smem = tcj::QNT * tcj::QBDEF * (int)sizeof(cplx);  // V panel
-        if (!c->qr_attr_set) {
-          CK(cudaFuncSetAttribute(tcj::qr_blocked_kernel<tcj::QNT, tcj::QBDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-          c->qr_attr_set = true;
-        }
         tcj::qr_blocked_kernel<tcj::QNT, tcj::QBDEF><<<dim3(nr, nb), tcj::QNT, smem, st>>>(d, a);
       } else if (d.n2 <= tcj::QMAXMW && !c->force_simple_jacobi) {
         const int smem = tcj::QNTW * tcj::QBDEF * (int)sizeof(cplx);  // V panel
-        if (!c->qrw_attr_set) {
-          CK(cudaFuncSetAttribute(tcj::qr_blocked_kernel<tcj::QNTW, tcj::QBDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-          c->qrw_attr_set = true;
-        }
         tcj::qr_blocked_kernel<tcj::QNTW, tcj::QBDEF><<<dim3(nr, nb), tcj::QNTW, smem, st>>>(d, a);
       } else {
         tcj::qr_kernel<<<dim3(nb, nr), tcj::NT, (d.n2 + 64) * sizeof(cplx), st>>>(d, a);
@@ -413,11 +426,6 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
         while (CS < 8 && (long long)nb * nr * CS * 2 <= (long long)c->sm_count * per_sm) CS *= 2;
         if (c->wide_cluster > 0) CS = c->wide_cluster;
         const size_t smem = tct::smem_bytes(d.n2);
-        if (!c->team_attr_set) {
-          CK(cudaFuncSetAttribute(tct::jacobi_team_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tct::smem_bytes(512)));
-          CK(cudaFuncSetAttribute(tct::jacobi_team_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tct::smem_bytes(256)));
-          c->team_attr_set = true;
-        }
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(nb * CS, nr);
         cfg.blockDim = dim3(tct::NT);
@@ -441,12 +449,7 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
       } else if (d.n2 > tcb::MAX_N && d.n2 <= 512 && !c->force_simple_jacobi && !c->old_wide) {
         if (launch_team(8)) return 1;
       } else if (d.n2 <= tcb::MAX_N && !c->force_simple_jacobi) {
-        const size_t smem = (size_t)3 * tcb::BR * d.n2 * sizeof(cplx) + d.n2 * sizeof(double2) + 64 + 2 * tcb::BR * sizeof(int);
-        if (!c->blocked_attr_set) {
-          CK(cudaFuncSetAttribute(tcb::jacobi_blocked_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          CK(cudaFuncSetAttribute(tcb::jacobi_blocked_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          c->blocked_attr_set = true;
-        }
+        const size_t smem = blocked_smem(d.n2);
         if (d.n2 <= 128 && !c->no_small_kernel)
           tcb::jacobi_blocked_kernel<4><<<dim3(nr, nb), tcb::NT, smem, st>>>(d, a);
         else
@@ -598,10 +601,6 @@ static int measure_range(tc_ctx *c, double *rdm, double *Z, double *ent, double 
     // (running this latency-bound chain on a side stream next to the bandwidth-bound measure kernel was measured:
     // 0.170 -> 0.167 ms per snapshot, not worth the extra streams and events)
     const size_t smem = (2 * (size_t)d.chi_cap + (tco::NT_OV / 32) * tco::OVC) * sizeof(cplx);
-    if (!c->ov_attr_set) {
-      CK(cudaFuncSetAttribute(tco::overlap_product_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      c->ov_attr_set = true;
-    }
     tco::overlap_product_kernel<<<dim3(nr, 2), tco::NT_OV, smem, st>>>(d, r_lo, ov, c->ovs, c->ovc);
     LAUNCHED();
   }
@@ -645,6 +644,8 @@ int tc_ctx_create2(int device, int L, int chi_cap, int R, int storage_only, void
   if (L < 1 || chi_cap < 1 || R < 1) return fail("tc_ctx_create: L, chi_cap, R must be >= 1");
   if (R > 65535) return fail("tc_ctx_create: R > 65535 chains per context");
   CK(cudaSetDevice(device));
+  if (ensure_kernel_attributes(device)) return 1;
+  if (chi_cap > 1024) return fail("tc_ctx_create: chi_cap > 1024");
   Layout lo = make_layout(L, chi_cap, R, storage_only != 0);
   tc_ctx *c = new tc_ctx();
   c->device = device;
