@@ -56,7 +56,8 @@ struct TcDev {
   // model
   const cplx *gates;  // [R][L-1][16]
   const cplx *kick;   // [R][4]
-  int rot64;          // TC_ROT64 A/B switches of the Jacobi kernel: bit 1 = barrier per round instead of the row hand-over
+  int rot64;          // TC_ROT64 A/B switches of the Jacobi kernel: bit 1 = barrier per round instead of the row hand-over,
+                      // bit 2 = no barrier between the visits of a pass (the last warp out stores and reloads the stage)
   int gates_diag;     // every gate of the model is diagonal (fused phase epilogue)
   double thr_sched[6];  // threshold Jacobi: sweeps 0..5 rotate only pairs with |g|^2 / (a_i a_j) above these
   double small_rel2;    // stopping rule: a sweep whose rotations all had |g|^2 / (a_i a_j) below this ends the iteration
