@@ -103,9 +103,11 @@ def test_wide_matrices_truncated_against_oracle(engine, cluster, monkeypatch):
     _compare(name, out, _oracle(name))
 
 
-def test_phase_diagram_point_shape_against_oracle(engine):
-    """BASELINE config 3's grid point: L = 24, chi_max = 64, 20 periods at eps = 0.1 (the two-CTA-per-SM narrow
-    instance of the Jacobi kernel)."""
+@pytest.mark.parametrize('small_kernel', ['0', '1'])
+def test_phase_diagram_point_shape_against_oracle(engine, small_kernel, monkeypatch):
+    """BASELINE config 3's grid point: L = 24, chi_max = 64, 20 periods at eps = 0.1, with the default 128-register
+    instance of the Jacobi kernel and with the two-CTAs-per-SM narrow instance (TC_SMALL_KERNEL=1)."""
+    monkeypatch.setenv('TC_SMALL_KERNEL', small_kernel)
     name = 'c3_L24_chi64'
     out = _gpu_schedule(name)
     _compare(name, out, _oracle(name))

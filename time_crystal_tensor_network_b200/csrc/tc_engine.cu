@@ -66,7 +66,10 @@ struct tc_ctx {
   cplx *ovs = nullptr;                               // [R][2][chi_cap] half vectors of overlap_product_kernel
   int *ovc = nullptr;                                // [R] arrival counters of its two CTAs per chain
   bool have_model = false;
-  bool no_small_kernel = false;  // TC_SMALL_KERNEL=0: the 128-register Jacobi kernel for narrow contexts too (A/B)
+  // TC_SMALL_KERNEL=1: the 64-register, two-CTAs-per-SM instance of the Jacobi kernel for contexts whose widest matrix has
+  // 128 columns.  It was the default in round 1 (+8 % at config 2); with the fast rotations it spills (312 B) and the
+  // 128-register instance is 6 % faster there (2271 -> 2408 chain-steps/s, r02), so that one now serves every width.
+  bool no_small_kernel = true;
   bool force_simple_jacobi = false;  // TC_JACOBI=simple: the warp-per-pair kernel for every size (A/B testing)
   bool old_theta = false;            // TC_THETA=v1: the policy-functor GEMM of round 1 for K1 (A/B testing)
   bool team_jacobi = false;          // TC_JACOBI=team: the two-warps-per-row kernel for the narrow matrices too (A/B testing)
