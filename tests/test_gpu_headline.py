@@ -103,6 +103,23 @@ def test_wide_matrices_truncated_against_oracle(engine, cluster, monkeypatch):
     _compare(name, out, _oracle(name))
 
 
+@pytest.mark.parametrize('case', ['wide_L18_chi256', 'headline_L32_chi128'])
+def test_qr_on_a_cluster_is_bit_identical(engine, case, monkeypatch):
+    """The blocked QR kernel on a thread-block cluster (TC_QR_CLUSTER CTAs per matrix; automatic for launches with few
+    matrices): every CTA factorises the panel with the same arithmetic and the trailing tiles are only dealt out
+    differently, so the triangular factor -- and with it every record of the run -- has the same bits for any cluster
+    size.  Both QR instances (256 and 512 rows), truncation active."""
+    name = case
+    monkeypatch.setenv('TC_GROUPS', '1')
+    outs = {}
+    for cs in ('1', '2', '4', '8'):
+        monkeypatch.setenv('TC_QR_CLUSTER', cs)
+        outs[cs] = _gpu_schedule(name)
+    for cs in ('2', '4', '8'):
+        for key in ('Z', 'S_ent', 'LE', 'chi'):
+            assert np.array_equal(outs['1'][key], outs[cs][key]), f'{name}: {key} differs between QR cluster 1 and {cs}'
+
+
 @pytest.mark.parametrize('small_kernel', ['0', '1'])
 def test_phase_diagram_point_shape_against_oracle(engine, small_kernel, monkeypatch):
     """BASELINE config 3's grid point: L = 24, chi_max = 64, 20 periods at eps = 0.1, with the default 128-register

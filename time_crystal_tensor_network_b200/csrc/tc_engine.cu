@@ -79,6 +79,7 @@ struct tc_ctx {
   int ngroups = 1;
   int sm_count = 148;
   int wide_cluster = 0;  // TC_WIDE_CLUSTER: CTAs per matrix of the wide (chi_cap > 128) Jacobi kernel, 0 = automatic
+  int qr_cluster = 0;    // TC_QR_CLUSTER: CTAs per matrix of the blocked QR kernel, 0 = automatic
   std::vector<cudaStream_t> gstreams;
   std::vector<cudaEvent_t> gjoin;
   cudaEvent_t gfork = nullptr;
@@ -409,12 +410,30 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
     }
     {
       ProfScope ps(c, TC_PROF_QR);
+      // a cluster of CS CTAs per matrix when the launch has too few matrices to fill the GPU (a single chain, config 4)
+      int CS = 1;
+      while (CS < 8 && (long long)nb * nr * CS * 2 <= (long long)c->sm_count) CS *= 2;
+      if (c->qr_cluster > 0) CS = c->qr_cluster;
+      auto launch_qr = [&](auto kern, int threads) -> int {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(nr * CS, nb);
+        cfg.blockDim = dim3(threads);
+        cfg.dynamicSmemBytes = (size_t)threads * tcj::QBDEF * sizeof(cplx);  // V panel
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CS;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, kern, d, a, CS));
+        return 0;
+      };
       if (d.n2 <= tcj::QMAXM && !c->force_simple_jacobi) {
-        const int smem = tcj::QNT * tcj::QBDEF * (int)sizeof(cplx);  // V panel
-        tcj::qr_blocked_kernel<tcj::QNT, tcj::QBDEF><<<dim3(nr, nb), tcj::QNT, smem, st>>>(d, a);
+        if (launch_qr(tcj::qr_blocked_kernel<tcj::QNT, tcj::QBDEF>, tcj::QNT)) return 1;
       } else if (d.n2 <= tcj::QMAXMW && !c->force_simple_jacobi) {
-        const int smem = tcj::QNTW * tcj::QBDEF * (int)sizeof(cplx);  // V panel
-        tcj::qr_blocked_kernel<tcj::QNTW, tcj::QBDEF><<<dim3(nr, nb), tcj::QNTW, smem, st>>>(d, a);
+        if (launch_qr(tcj::qr_blocked_kernel<tcj::QNTW, tcj::QBDEF>, tcj::QNTW)) return 1;
       } else {
         tcj::qr_kernel<<<dim3(nb, nr), tcj::NT, (d.n2 + 64) * sizeof(cplx), st>>>(d, a);
       }
@@ -675,6 +694,7 @@ int tc_ctx_create2(int device, int L, int chi_cap, int R, int storage_only, void
   if (const char *e = getenv("TC_SMALL_KERNEL")) c->no_small_kernel = atoi(e) == 0;
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
   if (const char *e = getenv("TC_WIDE_CLUSTER")) c->wide_cluster = atoi(e);
+  if (const char *e = getenv("TC_QR_CLUSTER")) c->qr_cluster = atoi(e);
   if (const char *e = getenv("TC_THETA")) c->old_theta = strcmp(e, "v1") == 0;
   if (const char *e = getenv("TC_GROUPS")) c->ngroups = atoi(e) > 0 ? atoi(e) : 1;
   if (const char *e = getenv("TC_JACOBI")) {

@@ -156,6 +156,15 @@ __device__ __forceinline__ void tcg_dmma(double &c0, double &c1, double a, doubl
                : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
 constexpr int QNT = 256, QMAXM = 256;    // fast-path instance: M <= 256 rows, 256 threads
 constexpr int QNTW = 512, QMAXMW = 512;  // wide instance (chi_cap <= 256): M <= 512 rows, 512 threads
 #ifndef TC_QR_U1
@@ -196,12 +205,19 @@ __device__ __forceinline__ void block_sum_vec(double (&v)[NV], double *scratch, 
     }
 }
 
-// QT threads = max rows, QB = panel width (multiple of 8); dynamic smem: V panel, QT * QB cplx
+// QT threads = max rows, QB = panel width (multiple of 8); dynamic smem: V panel, QT * QB cplx.
+// CS > 1: a thread-block cluster of CS CTAs shares one matrix (launches with too few matrices to fill the GPU: a single
+// chain, BASELINE config 4).  Every CTA factorises the panel redundantly (same arithmetic, same bits; only rank 0 writes
+// the R part back) and the 8-column tiles of the trailing matrix are dealt round-robin BY ABSOLUTE COLUMN BLOCK to the
+// CS * QT / 32 warps of the cluster, so a tile is read and written by the same SM for the whole factorisation (L1 is not
+// coherent between SMs); the only data that crosses SMs is the next panel, read with ld.cg after a cluster barrier.
 template <int QT, int QB>
-__global__ void __launch_bounds__(QT) qr_blocked_kernel(TcDev d, LayerArgs a) {
+__global__ void __launch_bounds__(QT) qr_blocked_kernel(TcDev d, LayerArgs a, int CS) {
   Bond b;
-  // blockIdx.x = chain, blockIdx.y = rank of the bond in centre-out order (largest matrices first)
-  if (!get_bond(d, a, centre_out(blockIdx.y, a.nb), blockIdx.x, b)) return;
+  // blockIdx.x / CS = chain, blockIdx.y = rank of the bond in centre-out order (largest matrices first); every CTA of a
+  // cluster sees the same bond, so the cluster leaves or stays as a whole
+  if (!get_bond(d, a, centre_out(blockIdx.y, a.nb), blockIdx.x / CS, b)) return;
+  const int crank = CS > 1 ? (int)cluster_rank() : 0;
   const int M = b.M, N = b.N;
   cplx *X = d.Xw + b.slot * d.slot_stride;
   extern __shared__ __align__(16) unsigned char qr_smem_raw[];
@@ -219,7 +235,8 @@ __global__ void __launch_bounds__(QT) qr_blocked_kernel(TcDev d, LayerArgs a) {
     const bool have = tid < rows;
     cplx p[QB];
 #pragma unroll
-    for (int j = 0; j < QB; ++j) p[j] = (have && j < pw) ? X[(size_t)(k0 + tid) * N + k0 + j] : cmake(0.0, 0.0);
+    for (int j = 0; j < QB; ++j)
+      p[j] = (have && j < pw) ? __ldcg(reinterpret_cast<const double2 *>(X + (size_t)(k0 + tid) * N + k0 + j)) : cmake(0.0, 0.0);
 #pragma unroll
     for (int j = 0; j < QB; ++j) {
       cplx tauj = cmake(0.0, 0.0);
@@ -264,7 +281,7 @@ __global__ void __launch_bounds__(QT) qr_blocked_kernel(TcDev d, LayerArgs a) {
       if (tid == 0) s_tau[j] = tauj;
     }
     // R part of the panel back to global
-    if (have)
+    if (have && crank == 0)
 #pragma unroll
       for (int j = 0; j < QB; ++j)
         if (j < pw) X[(size_t)(k0 + tid) * N + k0 + j] = p[j];
@@ -316,7 +333,11 @@ __global__ void __launch_bounds__(QT) qr_blocked_kernel(TcDev d, LayerArgs a) {
       const int ntiles = (ncols + 7) / 8;
       cplx *At = X + (size_t)k0 * N + k0 + QB;  // trailing block: row r (relative to k0), column cc (relative to k0 + QB)
       cplx *Ws = Wsm + warp * QB * 8;
-      for (int ct = warp; ct < ntiles; ct += QT / 32) {
+      // tile ct is the absolute 8-column block (k0 + QB) / 8 + ct: owner = block index modulo the warps of the cluster
+      constexpr int NWQ = QT / 32;
+      const int nwc = CS * NWQ, gw = crank * NWQ + warp;
+      const int ct0 = ((gw - (k0 + QB) / 8) % nwc + nwc) % nwc;
+      for (int ct = ct0; ct < ntiles; ct += nwc) {
         const int c0 = ct * 8;
         const bool cok = c0 + fr < ncols;
         double wre[MT][2], wim[MT][2];
@@ -376,7 +397,10 @@ __global__ void __launch_bounds__(QT) qr_blocked_kernel(TcDev d, LayerArgs a) {
         }
       }
     }
-    __syncthreads();
+    if (CS > 1)
+      cluster_sync_all();  // release / acquire at cluster scope: the next panel's columns are visible to every CTA
+    else
+      __syncthreads();
   }
 }
 
@@ -491,15 +515,6 @@ __global__ void __launch_bounds__(NT) jacobi_rows_kernel(TcDev d, LayerArgs a) {
 // (release / acquire, ~0.2 us) per round.  Scratch: the slot's `ww` row (squared norms, overwritten by the singular
 // values at the end) and its `knew` entry (rotation counter; finalize_kernel overwrites it).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ unsigned cluster_rank() {
-  unsigned r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-
 constexpr int WNPL = 16;  // complex elements per lane and row in the cluster kernel: matrices up to 512 columns
 
 __global__ void __launch_bounds__(NT) jacobi_rows_cluster_kernel(TcDev d, LayerArgs a, int CS) {
