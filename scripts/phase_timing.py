@@ -19,7 +19,14 @@ lib.tc_dbg_timing(out, 1)
 ens.ctx.floquet_step(1)
 lib.tc_dbg_timing(out, 1)
 v = np.array(list(out), dtype=float)
-if os.environ.get('TC_JACOBI', 'rb') == 'blocked':
+if os.environ.get('TCB_COARSE'):
+    # library built with -DTCB_TIMING -DTCB_COARSE: coarse phases of a sweep of the 16-warp kernel (warp 3, K = N = 256)
+    names = ['row norms at the sweep start', 'wait for the P block', 'internal pairs', 'wait for a q block',
+             'the 16 rounds of a visit', 'end-of-visit fence + barrier + store', 'P block back to global', 'kernel total']
+    for n, x in zip(names, v):
+        print(f'{n:40s} {x:.4g}  ({100 * x / v[7]:.1f} % of kernel)')
+    print('sum of phases / kernel total = %.3f' % (v[:7].sum() / v[7]))
+elif os.environ.get('TC_JACOBI', 'rb') == 'blocked':
     names = ['load+dot', 'warp reduce', 'rotation set-up', 'rotate+store', 'wait/barrier', 'pairs rotated', 'pairs visited', 'kernel total']
     for n, x in zip(names, v):
         print(f'{n:18s} {x:.4g}')

@@ -63,6 +63,22 @@ def test_observables_on_product_states():
     assert up.expectation_value('Sz', sites=[0])[0].real == pytest.approx(0.5)
 
 
+def test_physical_bounds_after_an_even_number_of_perfect_kicks():
+    """The reference's physical-bounds case (tests/test_physics_validation.py:195-220): L = 6, tau = 0.8, weak disorder,
+    ten periods with a perfect pi pulse -- the product state is back on the Neel state, the echo is 1 in exact arithmetic
+    and must not come out above 1.0; magnetisations stay inside their bounds."""
+    model = KickedIsingModel(n_sites=6, J=1.0, h_disorder=0.2, tau=0.8, disorder_seed=42)
+    psi = create_initial_state(6, 'neel')
+    for _ in range(10):
+        psi = model.floquet_step(psi)
+    for d in ('x', 'y', 'z'):
+        assert abs(magnetization(psi, d)) <= 6.0 + 1e-9
+        for site in range(3):
+            assert abs(magnetization(psi, d, site=site)) <= 1.0 + 1e-9
+    le = calculate_loschmidt_echo(create_initial_state(6, 'neel'), psi)
+    assert 0.0 <= le <= 1.0 and le > 1.0 - 1e-12
+
+
 def test_evolution_shapes_norms_and_timing():
     for L, limit in ((8, 0.1), (12, 0.5), (16, 2.0)):
         m = KickedIsingModel(L, 1.0, 0.3, 1.0, disorder_seed=42)
