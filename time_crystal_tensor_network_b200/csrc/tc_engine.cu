@@ -413,7 +413,7 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
       // a cluster of CS CTAs per matrix when the launch has too few matrices to fill the GPU (a single chain, config 4)
       int CS = 1;
       while (CS < 8 && (long long)nb * nr * CS * 2 <= (long long)c->sm_count) CS *= 2;
-      if (c->qr_cluster > 0) CS = c->qr_cluster;
+      if (c->qr_cluster > 0) CS = c->qr_cluster < 8 ? c->qr_cluster : 8;  // 8 = the portable cluster size limit
       auto launch_qr = [&](auto kern, int threads) -> int {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(nr * CS, nb);
