@@ -1,9 +1,11 @@
-"""Failure statistics of a Jacobi variant on one layer from a saturated state (see debug_team.py).
-usage: python scripts/debug_team_stat.py L chi prep reps VAR=VAL[,VAR=VAL] ..."""
+"""Failure statistics of a Jacobi variant on one layer from a saturated state.
+usage: python scripts/svd_stat_check.py L chi prep reps VAR=VAL[,VAR=VAL] ..."""
 import os
 import sys
 
 import numpy as np
+
+os.environ.setdefault('TC_ARENA', 'torch')   # the state is cloned arena to arena
 
 sys.path.insert(0, '.')
 from time_crystal_tensor_network_b200 import engine as eng

@@ -182,6 +182,7 @@ def test_svd_shortcuts_change_nothing_at_rounding_level(engine, switch, monkeypa
     below what the 1e-8 oracle comparisons could see.  Shortcuts: threshold sweeps (TC_THRESH=0 rotates every pair in
     every sweep), the quadratic-convergence stopping rule (TC_EARLY_STOP=0 runs the verification sweep)."""
     from time_crystal_tensor_network_b200 import engine as eng
+    monkeypatch.setenv('TC_ARENA', 'torch')                 # the state is cloned arena to arena below
     L, chi = 32, 128
     hs = np.array([eng.disorder_fields(L, 0.3, 1000)])
     kw = dict(epsilon=0.3, chi_max=chi, mode='tebd', svd_min=1e-12, trunc_cut=1e-7)
@@ -219,6 +220,7 @@ def test_svd_kernels_repeatedly_against_lapack(engine, L, chi, prep, variants, m
     from time_crystal_tensor_network_b200 import engine as eng
     from time_crystal_tensor_network_b200 import _lib
     monkeypatch.setenv('TC_GROUPS', '1')
+    monkeypatch.setenv('TC_ARENA', 'torch')                 # the state is cloned arena to arena below
     hs = np.array([eng.disorder_fields(L, 0.3, 11)])
     kw = dict(epsilon=0.3, chi_max=chi, mode='tebd', svd_min=1e-12, trunc_cut=1e-7)
     base = eng.FloquetEnsemble(L, 1.0, 1.0, hs, **kw)

@@ -177,3 +177,38 @@ def test_no_device_memory_left_behind():
     assert torch.cuda.memory_allocated() == base_alloc
     free1, _ = torch.cuda.mem_get_info()
     assert free0 - free1 < 64 << 20, f'{(free0 - free1) >> 20} MiB of device memory gone after 200 contexts'
+
+
+def test_library_owned_memory_without_torch():
+    """A process that never imports PyTorch (``python main.py``, the reference's scripts on the drop-in modules) runs on
+    arenas and streams owned by the library; the records have the bits of the torch-owned run, and torch stays out."""
+    import json
+    import subprocess
+    code = '''
+import sys, json, time
+t0 = time.perf_counter()
+sys.path.insert(0, %r)
+sys.path.insert(0, %r)
+import numpy as np, scipy.linalg
+from core.tensor_utils import create_initial_state
+from core.observables import magnetization, calculate_loschmidt_echo
+from models.kicked_ising import KickedIsingModel
+from dynamics.tebd_evolution import CustomFloquet
+model = KickedIsingModel(n_sites=10, J=1.0, h_disorder=0.3, tau=1.0, disorder_seed=3)
+model.pi_pulse_gate = scipy.linalg.expm(-1j * np.pi / 2 * 0.9 * model.sigma_x)
+psi0 = create_initial_state(10, 'neel')
+states, times, info = CustomFloquet(model, dict(chi_max=16)).evolve_floquet(psi0, 12)
+out = {'z': [magnetization(s, 'z', site=3) for s in states], 'le': [calculate_loschmidt_echo(psi0, s) for s in states],
+       'chi': [int(max(s.chi)) for s in states], 'torch': 'torch' in sys.modules, 'seconds': time.perf_counter() - t0}
+print(json.dumps(out))
+''' % (os.path.join(ROOT, 'src'), ROOT)
+    runs = {}
+    for mode in ('', 'torch'):
+        env = dict(os.environ, TC_ARENA=mode)
+        res = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=300)
+        assert res.returncode == 0, res.stderr[-2000:]
+        runs[mode] = json.loads(res.stdout.strip().splitlines()[-1])
+    assert runs['']['torch'] is False and runs['torch']['torch'] is True
+    for key in ('z', 'le', 'chi'):
+        assert runs[''][key] == runs['torch'][key], key
+    print('process wall time without / with torch: %.2f / %.2f s' % (runs['']['seconds'], runs['torch']['seconds']))

@@ -5,6 +5,8 @@ PyTorch is used only to own device memory and the CUDA stream; every computation
 libtc_b200.so through the C ABI of include/tc_b200.h.
 """
 import ctypes as C
+import os
+import sys
 
 import numpy as np
 
@@ -21,26 +23,43 @@ def _torch():
     return torch
 
 
+def _torch_owns_memory():
+    """Who owns a context's arena and stream.  PyTorch does when the process uses PyTorch anyway (bench.py, the sharded
+    drivers, anything that hands torch tensors to run_dev); a process that never imported it -- ``python main.py``, the
+    reference's scripts on the drop-in modules -- lets the library allocate (cudaMalloc / its own stream, the C ABI's
+    arena = NULL form) and saves the six seconds ``import torch`` costs.  TC_ARENA=torch | engine forces either."""
+    mode = os.environ.get('TC_ARENA', '')
+    if mode in ('torch', 'engine'):
+        return mode == 'torch'
+    return 'torch' in sys.modules
+
+
 class Context:
     """R independent chains of L sites, bond dimension at most chi_cap, on one GPU."""
 
     def __init__(self, L, chi_cap, R=1, device=0, storage_only=False):
         """storage_only: a context without SVD workspace (snapshots that are only measured, copied or overlapped);
         gate and Floquet calls on it raise."""
-        torch = _torch()
         self.lib = _lib.load()
         self.L, self.chi_cap, self.R, self.device = int(L), int(chi_cap), int(R), int(device)
         self.storage_only = bool(storage_only)
         nbytes = self.lib.tc_ctx_arena_bytes2(self.L, self.chi_cap, self.R, int(self.storage_only))
         if nbytes == 0:
             raise ValueError(f'invalid context shape L={L}, chi_cap={chi_cap}, R={R}')
-        self.stream = torch.cuda.Stream(device=self.device)
-        with torch.cuda.device(self.device):
-            self._arena = torch.empty(nbytes, dtype=torch.uint8, device=f'cuda:{self.device}')
         handle = C.c_void_p()
-        check(self.lib.tc_ctx_create2(self.device, self.L, self.chi_cap, self.R, int(self.storage_only),
-                                      self._arena.data_ptr(), nbytes, self.stream.cuda_stream, C.byref(handle)),
-              'tc_ctx_create2')
+        if _torch_owns_memory():
+            torch = _torch()
+            self.stream = torch.cuda.Stream(device=self.device)
+            with torch.cuda.device(self.device):
+                self._arena = torch.empty(nbytes, dtype=torch.uint8, device=f'cuda:{self.device}')
+            check(self.lib.tc_ctx_create2(self.device, self.L, self.chi_cap, self.R, int(self.storage_only),
+                                          self._arena.data_ptr(), nbytes, self.stream.cuda_stream, C.byref(handle)),
+                  'tc_ctx_create2')
+        else:
+            # arena and stream owned by the library (no CUDA device -> the call fails: there is no CPU fallback)
+            self.stream = self._arena = None
+            check(self.lib.tc_ctx_create2(self.device, self.L, self.chi_cap, self.R, int(self.storage_only),
+                                          None, 0, None, C.byref(handle)), 'tc_ctx_create2')
         self._h = handle
         self.arena_bytes = nbytes
 
