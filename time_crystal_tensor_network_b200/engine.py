@@ -23,6 +23,14 @@ def _torch():
     return torch
 
 
+def _echo(ov):
+    """|overlap|^2 with a rounding overshoot above 1 (a product state back on itself: 1 + 9e-16) returned as exactly 1,
+    as core.observables.calculate_loschmidt_echo does."""
+    le = np.abs(ov) ** 2
+    le[(le > 1.0) & (le < 1.0 + 1e-12)] = 1.0
+    return le
+
+
 def _torch_owns_memory():
     """Who owns a context's arena and stream.  PyTorch does when the process uses PyTorch anyway (bench.py, the sharded
     drivers, anything that hands torch tensors to run_dev); a process that never imported it -- ``python main.py``, the
@@ -342,7 +350,7 @@ class FloquetEnsemble:
             raise EngineError(f"bond dimension exceeded chi_cap={self.ctx.chi_cap} in {fl['chi_cap_overflow']} updates")
         if fl['svd_not_converged']:
             raise EngineError(f"{fl['svd_not_converged']} SVDs did not converge")
-        return {'Z': rec['Z'], 'S_ent': rec['ent'], 'overlap': ov, 'LE': np.abs(ov) ** 2, 'chi': rec['chi'],
+        return {'Z': rec['Z'], 'S_ent': rec['ent'], 'overlap': ov, 'LE': _echo(ov), 'chi': rec['chi'],
                 'periods': np.array(periods), 'flags': fl}
 
     def close(self):
