@@ -122,8 +122,9 @@ def test_qr_on_a_cluster_is_bit_identical(engine, case, monkeypatch):
 
 @pytest.mark.parametrize('small_kernel', ['0', '1'])
 def test_phase_diagram_point_shape_against_oracle(engine, small_kernel, monkeypatch):
-    """BASELINE config 3's grid point: L = 24, chi_max = 64, 20 periods at eps = 0.1, with the default 128-register
-    instance of the Jacobi kernel and with the two-CTAs-per-SM narrow instance (TC_SMALL_KERNEL=1)."""
+    """BASELINE config 3's grid point: L = 24, chi_max = 64, 20 periods at eps = 0.1, with the narrow instance of the
+    Jacobi kernel (row blocks of 8, two CTAs per SM: the default for chi_cap <= 64) and with the 16-warp instance
+    (TC_SMALL_KERNEL=0)."""
     monkeypatch.setenv('TC_SMALL_KERNEL', small_kernel)
     name = 'c3_L24_chi64'
     out = _gpu_schedule(name)

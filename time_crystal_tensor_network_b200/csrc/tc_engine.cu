@@ -66,10 +66,11 @@ struct tc_ctx {
   cplx *ovs = nullptr;                               // [R][2][chi_cap] half vectors of overlap_product_kernel
   int *ovc = nullptr;                                // [R] arrival counters of its two CTAs per chain
   bool have_model = false;
-  // TC_SMALL_KERNEL=1: the 64-register, two-CTAs-per-SM instance of the Jacobi kernel for contexts whose widest matrix has
-  // 128 columns.  It was the default in round 1 (+8 % at config 2); with the fast rotations it spills (312 B) and the
-  // 128-register instance is 6 % faster there (2271 -> 2408 chain-steps/s, r02), so that one now serves every width.
-  bool no_small_kernel = true;
+  // TC_SMALL_KERNEL=0: the 16-warp instance of the Jacobi kernel also for contexts whose widest matrix has 128 columns.
+  // Default: those contexts (chi_cap <= 64, BASELINE configs 2 and 3) run the instance with row blocks of 8 -- 8 warps, 128
+  // registers, two CTAs per SM (config 2: 2414 -> 2524 chain-steps/s).  History: round 1 had a 16-warp, 64-register,
+  // two-CTAs-per-SM instance here (+8 % then); with the fast rotations that one spilled (312 B) and lost 6 %.
+  bool no_small_kernel = false;
   bool force_simple_jacobi = false;  // TC_JACOBI=simple: the warp-per-pair kernel for every size (A/B testing)
   bool old_theta = false;            // TC_THETA=v1: the policy-functor GEMM of round 1 for K1 (A/B testing)
   bool team_jacobi = false;          // TC_JACOBI=team: the two-warps-per-row kernel for the narrow matrices too (A/B testing)
@@ -340,8 +341,8 @@ __global__ void __launch_bounds__(256) probe_dmma_kernel(double *out, int iters)
 // per context to that context's own size lets a small context lower it under a large one created earlier.)
 // ------------------------------------------------------------------------------------------------
 static constexpr size_t OV_SMEM_MAX = (2 * (size_t)1024 + (tco::NT_OV / 32) * tco::OVC) * sizeof(cplx);  // chi_cap <= 1024
-static size_t blocked_smem(int n2) {
-  return (size_t)3 * tcb::BR * n2 * sizeof(cplx) + (size_t)n2 * sizeof(double2) + 64 + 2 * tcb::BR * sizeof(int);
+static size_t blocked_smem(int n2, int br) {
+  return (size_t)3 * br * n2 * sizeof(cplx) + (size_t)n2 * sizeof(double2) + 64 + 2 * br * sizeof(int);
 }
 static int ensure_kernel_attributes(int device) {
   static std::atomic<unsigned long long> done{0};
@@ -352,8 +353,10 @@ static int ensure_kernel_attributes(int device) {
                           tcj::QNTW * tcj::QBDEF * (int)sizeof(cplx)));
   CK(cudaFuncSetAttribute(tct::jacobi_team_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tct::smem_bytes(512)));
   CK(cudaFuncSetAttribute(tct::jacobi_team_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tct::smem_bytes(256)));
-  CK(cudaFuncSetAttribute(tcb::jacobi_blocked_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blocked_smem(tcb::MAX_N)));
-  CK(cudaFuncSetAttribute(tcb::jacobi_blocked_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blocked_smem(tcb::MAX_N)));
+  CK(cudaFuncSetAttribute(tcb::jacobi_blocked_kernel<8, tcb::BR_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)blocked_smem(tcb::MAX_N, tcb::BR_WIDE)));
+  CK(cudaFuncSetAttribute(tcb::jacobi_blocked_kernel<4, tcb::BR_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)blocked_smem(tcb::MAX_N_NARROW, tcb::BR_NARROW)));
   CK(cudaFuncSetAttribute(tco::overlap_product_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OV_SMEM_MAX));
   if (device < 64) done.fetch_or(1ull << device);
   return 0;
@@ -471,11 +474,12 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
       } else if (d.n2 > tcb::MAX_N && d.n2 <= 512 && !c->force_simple_jacobi && !c->old_wide) {
         if (launch_team(8)) return 1;
       } else if (d.n2 <= tcb::MAX_N && !c->force_simple_jacobi) {
-        const size_t smem = blocked_smem(d.n2);
-        if (d.n2 <= 128 && !c->no_small_kernel)
-          tcb::jacobi_blocked_kernel<4><<<dim3(nr, nb), tcb::NT, smem, st>>>(d, a);
+        if (d.n2 <= tcb::MAX_N_NARROW && !c->no_small_kernel)  // row blocks of 8, two CTAs per SM
+          tcb::jacobi_blocked_kernel<4, tcb::BR_NARROW>
+              <<<dim3(nr, nb), tcb::BR_NARROW * 32, blocked_smem(d.n2, tcb::BR_NARROW), st>>>(d, a);
         else
-          tcb::jacobi_blocked_kernel<8><<<dim3(nr, nb), tcb::NT, smem, st>>>(d, a);
+          tcb::jacobi_blocked_kernel<8, tcb::BR_WIDE>
+              <<<dim3(nr, nb), tcb::BR_WIDE * 32, blocked_smem(d.n2, tcb::BR_WIDE), st>>>(d, a);
       } else {
         // wide matrices: a cluster of CS CTAs per matrix when the launch has too few matrices to fill the GPU
         int CS = 1;

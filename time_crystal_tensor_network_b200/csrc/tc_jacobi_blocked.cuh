@@ -21,12 +21,16 @@
 #include "tc_jacobi.cuh"
 
 namespace tcb {
-#ifndef TCB_BR
-#define TCB_BR 16
+// Rows per block = warps per CTA (one warp per row of a block), a template parameter of the kernel:
+//   16: the default -- 16 warps, 128 registers, three 64 KB stages at 256 columns, one CTA per SM;
+//    8: narrow contexts (widest matrix 128 columns, chi_cap <= 64: BASELINE configs 2 and 3) -- 8 warps, three 16 KB
+//       stages, TWO CTAs per SM at the same 128 registers: two independent matrices per SM, half as many internal pairs
+//       (+4.5 % at config 2; at 256 columns the same split costs 7 %: twice the block visits and L2 traffic).
+#ifndef TCB_NARROW_CTAS
+#define TCB_NARROW_CTAS 2  // resident CTAs per SM of the narrow instance (3: 80 registers, 16 B of spills, measured equal at config 2)
 #endif
-constexpr int NW = TCB_BR, NT = NW * 32, BR = TCB_BR;  // one warp per row of a block
-constexpr int CTAS_PER_SM = BR == 16 ? 1 : 2;
-constexpr int MAX_N = 256;
+constexpr int BR_WIDE = 16, BR_NARROW = 8;
+constexpr int MAX_N = 256, MAX_N_NARROW = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
@@ -256,8 +260,9 @@ __device__ __forceinline__ int pair_reg(cplx (&u)[NPL], cplx *xj, int N, int lan
   return big | (1 << 16);
 }
 
-template <int NPL, bool FULL>
+template <int NPL, bool FULL, int BR>
 __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int *s_rot, double *red) {
+  constexpr int NW = BR, NT = BR * 32;
   // carve the stage out of dynamic shared memory here so that the compiler keeps the shared address space
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // plain pointers computed from the shared array (no struct / array of pointers: an indexed pointer
@@ -552,12 +557,11 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
   }
 }
 
-// dynamic smem: 3 * BR * n2 cplx (P, Q0, Q1) + n2 double2 + 3 mbarriers (n2 <= MAX_N).
-// MAXNPL = 8: any matrix up to 256 columns, one CTA per SM (128 registers).  MAXNPL = 4: contexts whose widest matrix
-// has 128 columns (chi_cap <= 64: BASELINE configs 2 and 3) -- rows are half as long, 64 registers and 98 KB of shared
-// memory are enough, and two CTAs per SM hide each other's latency chains.
-template <int MAXNPL>
-__global__ void __launch_bounds__(NT, MAXNPL <= 4 ? 2 * CTAS_PER_SM : CTAS_PER_SM) jacobi_blocked_kernel(TcDev d, LayerArgs a) {
+// dynamic smem: 3 * BR * n2 cplx (P, Q0, Q1) + n2 double2 + 3 mbarriers + counters.
+// <MAXNPL = 8, BR = 16>: any matrix up to 256 columns, one CTA per SM.  <MAXNPL = 4, BR = 8>: contexts whose widest matrix
+// has 128 columns, two CTAs per SM.  Both 128 registers.
+template <int MAXNPL, int BR>
+__global__ void __launch_bounds__(BR * 32, BR == 16 ? 1 : TCB_NARROW_CTAS) jacobi_blocked_kernel(TcDev d, LayerArgs a) {
   Bond b;
   // blockIdx.x = chain, blockIdx.y = rank of the bond in centre-out order (largest matrices first)
   if (!get_bond(d, a, centre_out(blockIdx.y, a.nb), blockIdx.x, b)) return;
@@ -581,16 +585,16 @@ __global__ void __launch_bounds__(NT, MAXNPL <= 4 ? 2 * CTAS_PER_SM : CTAS_PER_S
   __syncthreads();
   const int npl = (N + 31) / 32;
   if (MAXNPL >= 8 && N == 256)
-    sweeps<8, true>(d, b, X, K, N, &s_rot, red);
+    sweeps<8, true, BR>(d, b, X, K, N, &s_rot, red);
   else if (npl <= 1)
-    sweeps<1, false>(d, b, X, K, N, &s_rot, red);
+    sweeps<1, false, BR>(d, b, X, K, N, &s_rot, red);
   else if (npl <= 2)
-    sweeps<2, false>(d, b, X, K, N, &s_rot, red);
+    sweeps<2, false, BR>(d, b, X, K, N, &s_rot, red);
   else if (MAXNPL <= 4 && N == 128)
-    sweeps<4, true>(d, b, X, K, N, &s_rot, red);
+    sweeps<4, true, BR>(d, b, X, K, N, &s_rot, red);
   else if (npl <= 4)
-    sweeps<4, false>(d, b, X, K, N, &s_rot, red);
+    sweeps<4, false, BR>(d, b, X, K, N, &s_rot, red);
   else if (MAXNPL >= 8)
-    sweeps<8, false>(d, b, X, K, N, &s_rot, red);
+    sweeps<8, false, BR>(d, b, X, K, N, &s_rot, red);
 }
 }  // namespace tcb
