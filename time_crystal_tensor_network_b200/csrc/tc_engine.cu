@@ -448,7 +448,9 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
         // a cluster of CS CTAs per matrix when the launch has too few matrices to fill the GPU
         const int per_sm = maxnpl <= 4 ? 2 : 1;
         int CS = 1;
-        while (CS < 8 && (long long)nb * nr * CS * 2 <= (long long)c->sm_count * per_sm) CS *= 2;
+        // from the context's shape, not from the chain group being launched: the cluster size fixes the pair order, and a
+        // context's results must not depend on TC_GROUPS / TC_WS_BYTES
+        while (CS < 8 && (long long)d.R * (d.L / 2) * CS * 2 <= (long long)c->sm_count * per_sm) CS *= 2;
         if (c->wide_cluster > 0) CS = c->wide_cluster;
         const size_t smem = tct::smem_bytes(d.n2);
         cudaLaunchConfig_t cfg = {};
@@ -474,7 +476,10 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
       } else if (d.n2 > tcb::MAX_N && d.n2 <= 512 && !c->force_simple_jacobi && !c->old_wide) {
         if (launch_team(8)) return 1;
       } else if (d.n2 <= tcb::MAX_N && !c->force_simple_jacobi) {
-        if (d.n2 <= tcb::MAX_N_NARROW && !c->no_small_kernel)  // row blocks of 8, two CTAs per SM
+        // row blocks of 8, two CTAs per SM: a throughput layout, for contexts with more matrices per layer than SMs.  The
+        // choice depends on the context's shape only (not on the chain group or chunk being launched), so a context's results
+        // do not depend on TC_GROUPS / TC_WS_BYTES; a single chain keeps the 16 warps per matrix (latency).
+        if (d.n2 <= tcb::MAX_N_NARROW && !c->no_small_kernel && (long long)d.R * (d.L / 2) > c->sm_count)
           tcb::jacobi_blocked_kernel<4, tcb::BR_NARROW>
               <<<dim3(nr, nb), tcb::BR_NARROW * 32, blocked_smem(d.n2, tcb::BR_NARROW), st>>>(d, a);
         else
