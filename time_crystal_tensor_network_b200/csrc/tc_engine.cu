@@ -71,6 +71,7 @@ struct tc_ctx {
   // registers, two CTAs per SM (config 2: 2414 -> 2524 chain-steps/s).  History: round 1 had a 16-warp, 64-register,
   // two-CTAs-per-SM instance here (+8 % then); with the fast rotations that one spilled (312 B) and lost 6 %.
   bool no_small_kernel = false;
+  bool force_small_kernel = false;   // TC_SMALL_KERNEL=2: the narrow instance for every context with chi_cap <= 64 (tests)
   bool force_simple_jacobi = false;  // TC_JACOBI=simple: the warp-per-pair kernel for every size (A/B testing)
   bool old_theta = false;            // TC_THETA=v1: the policy-functor GEMM of round 1 for K1 (A/B testing)
   bool team_jacobi = false;          // TC_JACOBI=team: the two-warps-per-row kernel for the narrow matrices too (A/B testing)
@@ -479,7 +480,8 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
         // row blocks of 8, two CTAs per SM: a throughput layout, for contexts with more matrices per layer than SMs.  The
         // choice depends on the context's shape only (not on the chain group or chunk being launched), so a context's results
         // do not depend on TC_GROUPS / TC_WS_BYTES; a single chain keeps the 16 warps per matrix (latency).
-        if (d.n2 <= tcb::MAX_N_NARROW && !c->no_small_kernel && (long long)d.R * (d.L / 2) > c->sm_count)
+        if (d.n2 <= tcb::MAX_N_NARROW && !c->no_small_kernel &&
+            (c->force_small_kernel || (long long)d.R * (d.L / 2) > c->sm_count))
           tcb::jacobi_blocked_kernel<4, tcb::BR_NARROW>
               <<<dim3(nr, nb), tcb::BR_NARROW * 32, blocked_smem(d.n2, tcb::BR_NARROW), st>>>(d, a);
         else
@@ -700,7 +702,10 @@ int tc_ctx_create2(int device, int L, int chi_cap, int R, int storage_only, void
   }
   c->arena_bytes = lo.total;
   c->ngroups = 4;
-  if (const char *e = getenv("TC_SMALL_KERNEL")) c->no_small_kernel = atoi(e) == 0;
+  if (const char *e = getenv("TC_SMALL_KERNEL")) {
+    c->no_small_kernel = atoi(e) == 0;
+    c->force_small_kernel = atoi(e) == 2;
+  }
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
   if (const char *e = getenv("TC_WIDE_CLUSTER")) c->wide_cluster = atoi(e);
   if (const char *e = getenv("TC_QR_CLUSTER")) c->qr_cluster = atoi(e);
