@@ -10,12 +10,14 @@ of chain 0 is handed to the CPU oracle (oracle/tebd_ref.py, the checker: one sin
 one more period; the GPU evolves the same period, the two are compared (max |delta| of <Z_i>, entropies) and timed.
 """
 import json
+import os
 import sys
 import time
 
 import numpy as np
 
-sys.path.insert(0, '.')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 from time_crystal_tensor_network_b200 import engine as eng  # noqa: E402
 
 import bench  # noqa: E402  (flop model)
@@ -43,28 +45,12 @@ def run_flops(chi_rec, periods):
 
 
 def cpu_check(ens, L, chi, eps):
-    """One more period of chain 0 on the GPU and on the CPU oracle from the same state."""
-    from oracle import tebd_ref   # checker and CPU baseline only
-    ctx = ens.ctx
-    Bs = [ctx.get_site(0, i) for i in range(L)]
-    Ss = [ctx.get_S(0, b) for b in range(L + 1)]
-    psi = tebd_ref.MPS([None] * L, Bs, Ss, [(0.0, 1.0)] * L)
-    kick = np.asarray(ens.kick[0])
-    gates = [ens.gates[0, i] for i in range(L - 1)]
-    trunc = dict(chi_max=chi, svd_min=1e-12, trunc_cut=1e-7)
-    t0 = time.time()
-    psi2, _ = tebd_ref.floquet_step(psi, kick, gates, mode='tebd', trunc=trunc)
-    t_cpu = time.time() - t0
-    t0 = time.time()
-    ctx.floquet_step(1)
-    ctx.sync()
-    t_gpu = time.time() - t0
-    rdm, ent = ctx.measure()
-    z = rdm[0, :, 0] - rdm[0, :, 1]
-    return {'cpu_oracle_s_per_period_chain0': round(t_cpu, 3), 'gpu_s_per_period_whole_ensemble': round(t_gpu, 4),
-            'max_abs_dZ': float(np.max(np.abs(z - tebd_ref.site_z(psi2)))),
-            'max_abs_dS': float(np.max(np.abs(ent[0] - psi2.entanglement_entropy()))),
-            'chi_equal': bool(list(ctx.chi()[0][1:-1]) == list(psi2.chi))}
+    """One more period of chain 0 on the GPU and on the CPU oracle from the same state (the checker lives with the tests:
+    tests/baseline_cpu_check.py -- nothing outside tests/, smoke() and bench.py's CPU legs touches oracle/)."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from baseline_cpu_check import one_period_against_oracle
+    return one_period_against_oracle(ens, L, chi)
+
 
 WHICH = [int(a) for a in sys.argv[1:] if a.isdigit()] or [1, 2, 3, 4, 5]
 
