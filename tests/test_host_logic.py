@@ -107,6 +107,36 @@ def test_product_never_imports_the_oracle():
                 assert 'oracle' not in open(os.path.join(base, f)).read(), f'{f} mentions the oracle'
 
 
+def test_only_tests_smoke_and_bench_import_the_oracle():
+    """oracle/ is test infrastructure: besides tests/ only __graft_entry__.smoke() and bench.py's CPU legs import it --
+    not main.py, not the drop-in modules under src/, not the scripts."""
+    import re
+    pat = re.compile(r'^\s*(from|import)\s+oracle\b', re.M)
+    offenders = []
+    for base in (ROOT, os.path.join(ROOT, 'scripts'), os.path.join(ROOT, 'src')):
+        for dirpath, dirs, files in os.walk(base):
+            if base == ROOT:
+                dirs[:] = []                       # top level only here; tests/ and oracle/ are excluded by construction
+            for f in files:
+                if f.endswith('.py') and pat.search(open(os.path.join(dirpath, f)).read()):
+                    offenders.append(os.path.relpath(os.path.join(dirpath, f), ROOT))
+    assert sorted(offenders) == ['__graft_entry__.py', 'bench.py'], offenders
+
+
+def test_no_cpu_fallback_on_library_owned_memory():
+    """The torch-free route (arena and stream owned by the library) fails as loudly without a GPU as the torch one."""
+    import subprocess
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from time_crystal_tensor_network_b200.engine import Context, EngineError\n"
+            "try:\n    Context(4, 2, 1)\nexcept EngineError as e:\n    print('EngineError')\n"
+            "print('torch' in sys.modules)\n" % ROOT)
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is visible')
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd='/', env=dict(os.environ, TC_ARENA=''))
+    assert out.returncode == 0 and out.stdout.split() == ['EngineError', 'False'], out.stdout + out.stderr
+
+
 def test_shard_bounds():
     from time_crystal_tensor_network_b200.sharding import shard_bounds, shard_sizes
     for n in (0, 1, 7, 32, 256, 1024, 1025):
