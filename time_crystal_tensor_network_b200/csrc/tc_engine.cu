@@ -85,6 +85,7 @@ struct tc_ctx {
   int sm_count = 148;
   int wide_cluster = 0;  // TC_WIDE_CLUSTER: CTAs per matrix of the wide (chi_cap > 128) Jacobi kernel, 0 = automatic
   int qr_cluster = 0;    // TC_QR_CLUSTER: CTAs per matrix of the blocked QR kernel, 0 = automatic
+  bool no_narrow_qr = false;  // TC_QR_NARROW=0: the 256-thread QR instance also for ensembles of narrow contexts (A/B)
   std::vector<cudaStream_t> gstreams;
   std::vector<cudaEvent_t> gjoin;
   cudaEvent_t gfork = nullptr;
@@ -353,6 +354,8 @@ static int ensure_kernel_attributes(int device) {
   if (device < 64 && (done.load() >> device) & 1ull) return 0;
   CK(cudaFuncSetAttribute(tcj::qr_blocked_kernel<tcj::QNT, tcj::QBDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           tcj::QNT * tcj::QBDEF * (int)sizeof(cplx)));
+  CK(cudaFuncSetAttribute(tcj::qr_blocked_kernel<tcj::QNTN, tcj::QBDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          tcj::QNTN * tcj::QBDEF * (int)sizeof(cplx)));
   CK(cudaFuncSetAttribute(tcj::qr_blocked_kernel<tcj::QNTW, tcj::QBDEF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           tcj::QNTW * tcj::QBDEF * (int)sizeof(cplx)));
   CK(cudaFuncSetAttribute(tct::jacobi_team_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tct::smem_bytes(512)));
@@ -439,7 +442,10 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
         CK(cudaLaunchKernelEx(&cfg, kern, d, a, CS));
         return 0;
       };
-      if (d.n2 <= tcj::QMAXM && !c->force_simple_jacobi) {
+      if (d.n2 <= tcj::QMAXMN && !c->force_simple_jacobi && !c->no_narrow_qr && (long long)d.R * (d.L / 2) > c->sm_count) {
+        // ensembles of narrow contexts: one thread per row still, 4 warps per CTA, more CTAs per SM; the same arithmetic
+        if (launch_qr(tcj::qr_blocked_kernel<tcj::QNTN, tcj::QBDEF>, tcj::QNTN)) return 1;
+      } else if (d.n2 <= tcj::QMAXM && !c->force_simple_jacobi) {
         if (launch_qr(tcj::qr_blocked_kernel<tcj::QNT, tcj::QBDEF>, tcj::QNT)) return 1;
       } else if (d.n2 <= tcj::QMAXMW && !c->force_simple_jacobi) {
         if (launch_qr(tcj::qr_blocked_kernel<tcj::QNTW, tcj::QBDEF>, tcj::QNTW)) return 1;
@@ -719,6 +725,7 @@ int tc_ctx_create2(int device, int L, int chi_cap, int R, int storage_only, void
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
   if (const char *e = getenv("TC_WIDE_CLUSTER")) c->wide_cluster = atoi(e);
   if (const char *e = getenv("TC_QR_CLUSTER")) c->qr_cluster = atoi(e);
+  if (const char *e = getenv("TC_QR_NARROW")) c->no_narrow_qr = atoi(e) == 0;
   if (const char *e = getenv("TC_THETA")) c->old_theta = strcmp(e, "v1") == 0;
   if (const char *e = getenv("TC_GROUPS")) c->ngroups = atoi(e) > 0 ? atoi(e) : 1;
   if (const char *e = getenv("TC_JACOBI")) {

@@ -166,6 +166,7 @@ __device__ __forceinline__ unsigned cluster_rank() {
 }
 
 constexpr int QNT = 256, QMAXM = 256;    // fast-path instance: M <= 256 rows, 256 threads
+constexpr int QNTN = 128, QMAXMN = 128;  // narrow instance: M <= 128 rows, 128 threads (ensembles with chi_cap <= 64); same bits
 constexpr int QNTW = 512, QMAXMW = 512;  // wide instance (chi_cap <= 256): M <= 512 rows, 512 threads
 #ifndef TC_QR_U1
 #define TC_QR_U1 4  // rows-of-4 steps of pass 1 of the trailing update in flight per warp
