@@ -120,12 +120,12 @@ def test_qr_on_a_cluster_is_bit_identical(engine, case, monkeypatch):
             assert np.array_equal(outs['1'][key], outs[cs][key]), f'{name}: {key} differs between QR cluster 1 and {cs}'
 
 
-@pytest.mark.parametrize('small_kernel', ['0', '2', '3'])
+@pytest.mark.parametrize('small_kernel', ['0', '2', '3', '4'])
 def test_phase_diagram_point_shape_against_oracle(engine, small_kernel, monkeypatch):
     """BASELINE config 3's grid point: L = 24, chi_max = 64, 20 periods at eps = 0.1, with every Jacobi kernel a narrow
-    context can run: the half-warp-row kernel (the default for ensembles with more matrices per layer than SMs, forced
-    here for the single chain with TC_SMALL_KERNEL=3), the 16-warp instance (=0, what a single chain runs) and the
-    full-warp instance with row blocks of 8 (=2)."""
+    context can run: the half-warp-row kernel in its 8-warp instance (the default for ensembles with more matrices per
+    layer than SMs, forced here for the single chain with TC_SMALL_KERNEL=3) and its 16-warp instance (=4, what a
+    single chain runs by default), the full-warp 16-warp kernel (=0) and its instance with row blocks of 8 (=2)."""
     monkeypatch.setenv('TC_SMALL_KERNEL', small_kernel)
     name = 'c3_L24_chi64'
     out = _gpu_schedule(name)
@@ -210,7 +210,7 @@ def test_svd_shortcuts_change_nothing_at_rounding_level(engine, switch, monkeypa
 
 
 @pytest.mark.parametrize('L,chi,prep,variants', [
-    (14, 64, 8, ['TC_SMALL_KERNEL=3', 'TC_SMALL_KERNEL=2', 'TC_SMALL_KERNEL=0']),   # 128 columns: half-warp rows, blocks of 8 / 16
+    (14, 64, 8, ['TC_SMALL_KERNEL=3', 'TC_SMALL_KERNEL=4', 'TC_SMALL_KERNEL=2', 'TC_SMALL_KERNEL=0']),   # 128 columns: half-warp rows (8 / 16 warps), full-warp rows in blocks of 8 / 16
     (16, 128, 9, ['TC_JACOBI=blocked', 'TC_JACOBI=team']),
     (18, 256, 10, ['TC_WIDE_CLUSTER=1', 'TC_WIDE_CLUSTER=4', 'TC_WIDE_CLUSTER=8', 'TC_JACOBI=wide_v1']),
 ])

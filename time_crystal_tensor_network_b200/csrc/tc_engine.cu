@@ -67,11 +67,12 @@ struct tc_ctx {
   cplx *ovs = nullptr;                               // [R][2][chi_cap] half vectors of overlap_product_kernel
   int *ovc = nullptr;                                // [R] arrival counters of its two CTAs per chain
   bool have_model = false;
-  // TC_SMALL_KERNEL=0: the 16-warp instance of the Jacobi kernel also for contexts whose widest matrix has 128 columns.
-  // Default: ensembles of such contexts (chi_cap <= 64, BASELINE configs 2 and 3) run the half-warp-row kernel, two CTAs
-  // per SM (config 2's shape: 2410 -> 2914 chain-steps/s).  =2: the full-warp instance with row blocks of 8 (2504), =3: the
-  // half-warp kernel also for single chains (tests).  History: round 1 had a 16-warp, 64-register, two-CTAs-per-SM instance
-  // here (+8 % then); with the fast rotations that one spilled (312 B) and lost 6 %.
+  // TC_SMALL_KERNEL=0: the full-warp 16-warp instance of the Jacobi kernel also for contexts whose widest matrix has 128
+  // columns.  Default: such contexts (chi_cap <= 64, BASELINE configs 2 and 3) run the half-warp-row kernel -- ensembles
+  // its 8-warp instance, two CTAs per SM (config 2's shape: 2410 -> 2914 chain-steps/s), single chains its 16-warp instance.
+  // =2: the full-warp instance with row blocks of 8 (2504), =3 / =4: force the 8-warp / 16-warp half-warp instance (tests).
+  // History: round 1 had a 16-warp, 64-register, two-CTAs-per-SM instance here (+8 % then); with the fast rotations that
+  // one spilled (312 B) and lost 6 %.
   bool no_small_kernel = false;
   bool force_small_kernel = false;   // TC_SMALL_KERNEL=2: the narrow instance for every context with chi_cap <= 64 (tests)
   int halfwarp_kernel = 0;           // TC_SMALL_KERNEL=3: the half-warp-row kernel for every narrow context (A/B, tests)
@@ -364,8 +365,10 @@ static int ensure_kernel_attributes(int device) {
                           (int)blocked_smem(tcb::MAX_N, tcb::BR_WIDE)));
   CK(cudaFuncSetAttribute(tcb::jacobi_blocked_kernel<4, tcb::BR_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                           (int)blocked_smem(tcb::MAX_N_NARROW, tcb::BR_NARROW)));
-  CK(cudaFuncSetAttribute(tchw::jacobi_halfwarp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          (int)tchw::smem_bytes(tchw::MAX_N)));
+  CK(cudaFuncSetAttribute(tchw::jacobi_halfwarp_kernel<tchw::NW_MANY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)tchw::smem_bytes(tchw::MAX_N, tchw::NW_MANY)));
+  CK(cudaFuncSetAttribute(tchw::jacobi_halfwarp_kernel<tchw::NW_ONE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)tchw::smem_bytes(tchw::MAX_N, tchw::NW_ONE)));
   CK(cudaFuncSetAttribute(tco::overlap_product_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OV_SMEM_MAX));
   if (device < 64) done.fetch_or(1ull << device);
   return 0;
@@ -488,14 +491,20 @@ static int run_bonds(tc_ctx *c, int first_site, int nb, int r_lo, int r_hi, int 
       } else if (d.n2 > tcb::MAX_N && d.n2 <= 512 && !c->force_simple_jacobi && !c->old_wide) {
         if (launch_team(8)) return 1;
       } else if (d.n2 <= tcb::MAX_N && !c->force_simple_jacobi) {
-        // Narrow contexts (widest matrix 128 columns) with more matrices per layer than SMs run the half-warp-row kernel
-        // (tc_jacobi_halfwarp.cuh): a throughput layout.  The choice depends on the context's shape only (not on the chain
-        // group or chunk being launched), so a context's results do not depend on TC_GROUPS / TC_WS_BYTES; a single chain
-        // keeps the 16 warps per matrix (latency: 12.5 against 15.0 ms of Jacobi per period at L = 16, chi = 64).
+        // Narrow contexts (widest matrix 128 columns) run the half-warp-row kernel (tc_jacobi_halfwarp.cuh): with more
+        // matrices per layer than SMs its 8-warp instance, two CTAs per SM (throughput); otherwise (a single chain) the
+        // 16-warp instance, 32 half-warps on one matrix (Jacobi of one period at L = 16, chi = 64: 10.9 ms against 12.5 ms
+        // on full-warp rows and 15.0 ms on the 8-warp instance).  The choice depends on the context's shape only (not on
+        // the chain group or chunk being launched), so a context's results do not depend on TC_GROUPS / TC_WS_BYTES.
         const bool narrow = d.n2 <= tchw::MAX_N && !c->no_small_kernel;
         const bool many = (long long)d.R * (d.L / 2) > c->sm_count;
-        if (narrow && (c->halfwarp_kernel || (many && !c->force_small_kernel)))  // rows on half-warps, two CTAs per SM
-          tchw::jacobi_halfwarp_kernel<<<dim3(nr, nb), tchw::NT, tchw::smem_bytes(d.n2), st>>>(d, a);
+        const bool automatic = !c->force_small_kernel && !c->halfwarp_kernel;
+        if (narrow && (c->halfwarp_kernel == 3 || (automatic && many)))
+          tchw::jacobi_halfwarp_kernel<tchw::NW_MANY>  // rows on half-warps, 8 warps, two CTAs per SM: throughput
+              <<<dim3(nr, nb), tchw::NW_MANY * 32, tchw::smem_bytes(d.n2, tchw::NW_MANY), st>>>(d, a);
+        else if (narrow && (c->halfwarp_kernel == 4 || automatic))
+          tchw::jacobi_halfwarp_kernel<tchw::NW_ONE>  // 16 warps = 32 half-warps on one matrix: latency of a single chain
+              <<<dim3(nr, nb), tchw::NW_ONE * 32, tchw::smem_bytes(d.n2, tchw::NW_ONE), st>>>(d, a);
         else if (narrow && c->force_small_kernel)  // TC_SMALL_KERNEL=2 (A/B): full-warp rows in blocks of 8
           tcb::jacobi_blocked_kernel<4, tcb::BR_NARROW>
               <<<dim3(nr, nb), tcb::BR_NARROW * 32, blocked_smem(d.n2, tcb::BR_NARROW), st>>>(d, a);
@@ -720,7 +729,7 @@ int tc_ctx_create2(int device, int L, int chi_cap, int R, int storage_only, void
   if (const char *e = getenv("TC_SMALL_KERNEL")) {
     c->no_small_kernel = atoi(e) == 0;
     c->force_small_kernel = atoi(e) == 2;
-    c->halfwarp_kernel = atoi(e) == 3;
+    c->halfwarp_kernel = (atoi(e) == 3 || atoi(e) == 4) ? atoi(e) : 0;
   }
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
   if (const char *e = getenv("TC_WIDE_CLUSTER")) c->wide_cluster = atoi(e);

@@ -32,10 +32,9 @@ using tcb::Rot;
 using tcb::rot_apply;
 using tcb::smem_u32;
 
-#ifndef TCHW_NW
-#define TCHW_NW 8  // warps per CTA: 8 = 16 half-warps, row blocks of 16, two CTAs per SM; 16 = row blocks of 32, one CTA per SM
-#endif
-constexpr int NW = TCHW_NW, NT = NW * 32, BR = 2 * NW;
+// warps per CTA, a template parameter: 8 = 16 half-warps, row blocks of 16, two CTAs per SM (ensembles: throughput);
+// 16 = 32 half-warps, row blocks of 32, one CTA per SM (a single chain: all 32 pairs in flight work on ONE matrix)
+constexpr int NW_MANY = 8, NW_ONE = 16;
 constexpr int MAX_N = 128;
 constexpr unsigned FULLM = 0xffffffffu;
 
@@ -134,8 +133,9 @@ __device__ __forceinline__ int pair_reg_h(bool active, cplx (&u)[NPL], cplx *xj,
   return big | ((int)rot << 16);
 }
 
-template <int NPL, bool FULL>
+template <int NPL, bool FULL, int NW>
 __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int *s_rot, double *red) {
+  constexpr int NT = NW * 32, BR = 2 * NW;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cplx *const sP = reinterpret_cast<cplx *>(smem_raw);
   cplx *const sQ = sP + (size_t)BR * N;  // Q[buf] = sQ + buf * BR * N
@@ -322,11 +322,13 @@ __device__ void sweeps(const TcDev &d, const Bond &b, cplx *X, int K, int N, int
   }
 }
 
-__host__ __device__ inline size_t smem_bytes(int n2) {
-  return (size_t)3 * BR * n2 * sizeof(cplx) + (size_t)n2 * sizeof(double2) + 64 + 2 * BR * sizeof(int);
+__host__ __device__ inline size_t smem_bytes(int n2, int nw) {
+  return (size_t)3 * 2 * nw * n2 * sizeof(cplx) + (size_t)n2 * sizeof(double2) + 64 + 2 * 2 * nw * sizeof(int);
 }
 
-__global__ void __launch_bounds__(NT, NW == 8 ? 2 : 1) jacobi_halfwarp_kernel(TcDev d, LayerArgs a) {
+template <int NW>
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1) jacobi_halfwarp_kernel(TcDev d, LayerArgs a) {
+  constexpr int BR = 2 * NW;
   Bond b;
   // blockIdx.x = chain, blockIdx.y = rank of the bond in centre-out order (largest matrices first)
   if (!get_bond(d, a, centre_out(blockIdx.y, a.nb), blockIdx.x, b)) return;
@@ -346,14 +348,14 @@ __global__ void __launch_bounds__(NT, NW == 8 ? 2 : 1) jacobi_halfwarp_kernel(Tc
   __syncthreads();
   const int npl = (N + 15) / 16;
   if (N == 128)
-    sweeps<8, true>(d, b, X, K, N, &s_rot, red);
+    sweeps<8, true, NW>(d, b, X, K, N, &s_rot, red);
   else if (npl <= 1)
-    sweeps<1, false>(d, b, X, K, N, &s_rot, red);
+    sweeps<1, false, NW>(d, b, X, K, N, &s_rot, red);
   else if (npl <= 2)
-    sweeps<2, false>(d, b, X, K, N, &s_rot, red);
+    sweeps<2, false, NW>(d, b, X, K, N, &s_rot, red);
   else if (npl <= 4)
-    sweeps<4, false>(d, b, X, K, N, &s_rot, red);
+    sweeps<4, false, NW>(d, b, X, K, N, &s_rot, red);
   else
-    sweeps<8, false>(d, b, X, K, N, &s_rot, red);
+    sweeps<8, false, NW>(d, b, X, K, N, &s_rot, red);
 }
 }  // namespace tchw
