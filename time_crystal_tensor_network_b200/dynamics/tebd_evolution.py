@@ -94,7 +94,8 @@ class TEBDEvolution:
     def _trotter(self, psi_initial: MPS, n_steps: int, prefactor, observe_every: int, dt: float):
         """n_steps second-order Trotter steps G_even(dt/2) G_odd(dt) G_even(dt/2) with bond gates
         expm(prefactor * dt * H_b): prefactor = -1j is real time, -1 is imaginary time (the state is
-        renormalised by every update, so non-unitary gates need no extra care)."""
+        renormalised by every update; the O(dt) loss of canonical form under non-unitary gates is repaired by the
+        caller, imaginary_time_evolution, with MPS.canonical_form)."""
         terms = self._bond_terms()
         L = psi_initial.L
         if len(terms) != L - 1:
@@ -145,17 +146,23 @@ class TEBDEvolution:
         states, times, info, _ = self._trotter(psi_initial, int(total_time / self.dt), -1j, observe_every, self.dt)
         return states, times, info
 
-    def imaginary_time_evolution(self, psi_initial: MPS, dts=(0.1, 0.05, 0.02, 0.01), steps_per_dt: int = 100) -> Tuple[MPS, Dict]:
+    def imaginary_time_evolution(self, psi_initial: MPS, dts=(0.1, 0.05, 0.02, 0.01), steps_per_dt: int = 100,
+                                 recanonicalize: bool = True) -> Tuple[MPS, Dict]:
         """Ground-state preparation by imaginary-time TEBD (the README's claim, BASELINE config 5): for every dt of
-        the schedule, ``steps_per_dt`` second-order steps of exp(-dt H).  Returns (psi, info) with the energy
-        after every stage (sum of <H_b>)."""
+        the schedule, ``steps_per_dt`` second-order steps of exp(-dt H).  Non-unitary gates leave the chain out of
+        canonical form at O(dt); every stage therefore ends with ``MPS.canonical_form()`` (identity-gate sweeps, the
+        state itself unchanged), so that the energies, the Schmidt values and whatever evolution follows start from an
+        exactly canonical chain.  ``recanonicalize=False`` keeps the plain TEBD behaviour (what TeNPy's TEBDEngine
+        does by itself).  Returns (psi, info) with the energy after every stage (sum of <H_b>)."""
         psi = psi_initial
-        energies, chis = [], []
+        energies, chis, sweeps = [], [], []
         for dt in dts:
             _, _, _, psi = self._trotter(psi, steps_per_dt, -1.0, max(steps_per_dt, 1), dt)
+            if recanonicalize:
+                sweeps.append(psi.canonical_form())
             energies.append(self.energy(psi))
             chis.append(max(psi.chi) if psi.chi else 1)
-        return psi, {'energies': energies, 'bond_dimensions': chis, 'dts': list(dts)}
+        return psi, {'energies': energies, 'bond_dimensions': chis, 'dts': list(dts), 'canonical_sweeps': sweeps}
 
     def energy(self, psi: MPS) -> float:
         """<H> = sum_b <H_b> through the Pauli expansion of every bond term (two-point correlators on the device)."""

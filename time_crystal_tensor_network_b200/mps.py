@@ -182,6 +182,52 @@ class MPS:
             raise NotImplementedError('only 1- and 2-site operators')
         self._touch()
 
+    def canonical_form(self, renormalize=True, tol=1e-13, max_sweeps=None):
+        """Bring the chain back to canonical form after non-unitary gates (TeNPy: ``MPS.canonical_form``).
+
+        The TEBD update of a bond assumes orthonormal surroundings; a non-unitary gate (imaginary time) breaks that for
+        its neighbours at O(dt), and single-site expectation values / Schmidt values read off the tensors are then off
+        by as much.  Sweeps of IDENTITY gates without truncation repair it with the kernels the evolution uses: the SVD
+        of an identity update re-orthonormalises the two tensors of a bond and replaces its Schmidt values, the state
+        itself (the product of the B tensors) does not change, and every even + odd sweep carries the orthonormality
+        one bond further, so a finite chain is exactly canonical after at most L/2 + 1 sweeps and a short-range
+        correlated one much earlier (NumPy model: tests/studies/recanonicalise_identity_layers.py).  The sweeps stop
+        once no Schmidt value moves by more than ``tol``.  The model and the truncation rule of the context are
+        overwritten (every evolution call sets its own).  The state comes back normalised (the kernels renormalise
+        every update and do not keep the factor), hence ``renormalize=False`` is refused.  Returns the number of
+        sweeps made."""
+        if not renormalize:
+            raise NotImplementedError('canonical_form keeps no norm factor: only renormalize=True')
+        L = self.L
+        if L < 2:
+            return 0
+        chi = self._chi_full()
+        self._grow(max(chi))
+        ctx = self._ctx
+        ctx.set_model(np.eye(4, dtype=complex).reshape(1, 1, 4, 4).repeat(L - 1, axis=1),
+                      np.eye(2, dtype=complex).reshape(1, 2, 2))
+        # no bond can grow under identity gates; 1e-14 (relative) only drops the numerically zero directions
+        ctx.set_trunc('tebd', chi_max=max(chi), svd_min=1e-14, trunc_cut=0.0)
+        if max_sweeps is None:
+            max_sweeps = L // 2 + 2
+        schmidt = lambda: [ctx.get_S(0, b) for b in range(1, L)]
+        old, sweeps = schmidt(), 0
+        for sweeps in range(1, max_sweeps + 1):
+            ctx.apply_layer(0, 0)
+            if L > 2:
+                ctx.apply_layer(1, 0)
+            new = schmidt()
+            moved = max((np.max(np.abs(a - b)) if a.shape == b.shape else np.inf) for a, b in zip(old, new))
+            old = new
+            if moved <= tol:
+                break
+        fl = ctx.flags()
+        if fl['chi_cap_overflow'] or fl['svd_not_converged']:
+            raise EngineError(f'canonical_form failed on the device: {fl}')
+        self.norm = 1.0
+        self._touch()
+        return sweeps
+
     # ------------------------------------------------------------------ observables
     def _rdm(self):
         if 'rdm' not in self._cache:
