@@ -11,7 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libtc_b200.so')
 SOURCES = ['tc_engine.cu']
-HEADERS = ['tc_common.cuh', 'tc_gemm.cuh', 'tc_theta.cuh', 'tc_jacobi.cuh', 'tc_jacobi_blocked.cuh', 'tc_jacobi_team.cuh', 'tc_observe.cuh']
+HEADERS = ['tc_common.cuh', 'tc_gemm.cuh', 'tc_theta.cuh', 'tc_jacobi.cuh', 'tc_jacobi_blocked.cuh', 'tc_jacobi_halfwarp.cuh',
+           'tc_jacobi_team.cuh', 'tc_observe.cuh']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
 
